@@ -1,0 +1,5 @@
+"""CPU oracle for the MinLZ hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this package.  The product (minlz_b200) never does.
+"""

@@ -1,0 +1,977 @@
+/*
+ * minlz_oracle.c -- CPU restatement of the MinLZ block codec (pure-Go path).
+ *
+ * TEST INFRASTRUCTURE ONLY: see minlz_oracle.h.  Every function cites the
+ * reference file:line it follows (paths relative to the minio/minlz tree).
+ * Encoder byte output: "parity unpinned" (no reference fixture pins it); the
+ * decoder and the emitters are pinned by tests/test_oracle_golden.py.
+ */
+#include "minlz_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- encode.go:30-58 constants ---------------------------------------- */
+enum {
+    kMaxCopy1Offset = 1024,
+    kMinCopy2Offset = 64,
+    kMaxCopy2Offset = 64 + 65535,
+    kCopy2LitMaxLen = 7 + 4,
+    kMaxCopy2Lits = 4,
+    kMaxCopy3Lits = 3,
+    kMinCopy3Offset = 65536,
+    kMaxCopy3Offset = (2 << 20) + 65535,
+    kInputMargin = 8,            /* encode.go:216 */
+    kMinNonLiteralBlockSize = 16 /* encode.go:220 */
+};
+
+/* minlz.go:68-75 tags */
+enum { TAG_LITERAL = 0, TAG_REPEAT = 4, TAG_COPY1 = 1, TAG_COPY2 = 2, TAG_COPY3 = 7, TAG_COPY2_FUSED = 3 };
+
+/* ---- unsafe_enabled.go:26-60 little-endian unaligned access ------------ */
+static inline uint16_t ld16(const uint8_t *b, int64_t i) { uint16_t v; memcpy(&v, b + i, 2); return v; }
+static inline uint32_t ld32(const uint8_t *b, int64_t i) { uint32_t v; memcpy(&v, b + i, 4); return v; }
+static inline uint64_t ld64(const uint8_t *b, int64_t i) { uint64_t v; memcpy(&v, b + i, 8); return v; }
+static inline void st16(uint8_t *b, int64_t i, uint16_t v) { memcpy(b + i, &v, 2); }
+static inline void st32(uint8_t *b, int64_t i, uint32_t v) { memcpy(b + i, &v, 4); }
+
+/* ---- hashes: encode_l1.go:26-29, encode_l2.go:25-49 -------------------- */
+static inline uint32_t hash4(uint64_t u, int h) { return ((uint32_t)u * 2654435761u) >> (32 - h); }
+static inline uint32_t hash5(uint64_t u, int h) { return (uint32_t)(((u << 24) * 889523592379ull) >> (64 - h)); }
+static inline uint32_t hash6(uint64_t u, int h) { return (uint32_t)(((u << 16) * 227718039650203ull) >> (64 - h)); }
+static inline uint32_t hash7(uint64_t u, int h) { return (uint32_t)(((u << 8) * 58295818150454627ull) >> (64 - h)); }
+
+static inline uint32_t hashN(uint64_t u, int h, int nbytes) {
+    switch (nbytes) {
+    case 4: return hash4(u, h);
+    case 5: return hash5(u, h);
+    case 6: return hash6(u, h);
+    default: return hash7(u, h);
+    }
+}
+
+/* encode.go:234-244 MaxEncodedLen */
+int64_t mzo_max_encoded_len(int64_t src_len) {
+    if (src_len < 0 || (uint64_t)src_len > MZO_MAX_BLOCK_SIZE) return -1;
+    if (src_len == 0) return 1;
+    return src_len + 2;
+}
+
+/* ---- emitters ---------------------------------------------------------- */
+
+/* asm_none.go:84-122 emitLiteral */
+int mzo_emit_literal(uint8_t *dst, const uint8_t *lit, size_t len) {
+    if (len == 0) return 0;
+    uint32_t n = (uint32_t)(len - 1);
+    int i;
+    if (n < 29) {
+        dst[0] = (uint8_t)(n << 3) | TAG_LITERAL;
+        i = 1;
+    } else if (n < (1u << 8) + 29) {
+        dst[1] = (uint8_t)(n - 29);
+        dst[0] = 29 << 3 | TAG_LITERAL;
+        i = 2;
+    } else if (n < (1u << 16) + 29) {
+        n -= 29;
+        dst[2] = (uint8_t)(n >> 8);
+        dst[1] = (uint8_t)n;
+        dst[0] = 30 << 3 | TAG_LITERAL;
+        i = 3;
+    } else {
+        n -= 29;
+        dst[3] = (uint8_t)(n >> 16);
+        dst[2] = (uint8_t)(n >> 8);
+        dst[1] = (uint8_t)n;
+        dst[0] = 31 << 3 | TAG_LITERAL;
+        i = 4;
+    }
+    memcpy(dst + i, lit, len);
+    return i + (int)len;
+}
+
+/* asm_none.go:125-156 emitRepeat */
+int mzo_emit_repeat(uint8_t *dst, int length) {
+    if (length < 30) {
+        dst[0] = (uint8_t)((length - 1) << 3) | TAG_REPEAT;
+        return 1;
+    }
+    length -= 30;
+    if (length < 256) {
+        dst[1] = (uint8_t)length;
+        dst[0] = 29 << 3 | TAG_REPEAT;
+        return 2;
+    }
+    if (length < 65536) {
+        dst[2] = (uint8_t)(length >> 8);
+        dst[1] = (uint8_t)length;
+        dst[0] = 30 << 3 | TAG_REPEAT;
+        return 3;
+    }
+    dst[3] = (uint8_t)(length >> 16);
+    dst[2] = (uint8_t)(length >> 8);
+    dst[1] = (uint8_t)length;
+    dst[0] = 31 << 3 | TAG_REPEAT;
+    return 4;
+}
+
+/* asm_none.go:160-200 encodeCopy3 (also the expanded copy in emitCopy :221-258) */
+static int encode_copy3(uint8_t *dst, int offset, int length, int lits) {
+    length -= 4;
+    uint32_t enc = (uint32_t)(offset - 65536) << 11 | TAG_COPY3 | (uint32_t)(lits << 3);
+    if (length <= 60) {
+        enc |= (uint32_t)(length << 5);
+        st32(dst, 0, enc);
+        return 4;
+    }
+    length -= 60;
+    if (length < 256) {
+        dst[4] = (uint8_t)length;
+        enc |= 61 << 5;
+        st32(dst, 0, enc);
+        return 5;
+    }
+    if (length < 65536) {
+        enc |= 62 << 5;
+        dst[5] = (uint8_t)(length >> 8);
+        dst[4] = (uint8_t)length;
+        st32(dst, 0, enc);
+        return 6;
+    }
+    enc |= 63 << 5;
+    dst[6] = (uint8_t)(length >> 16);
+    dst[5] = (uint8_t)(length >> 8);
+    dst[4] = (uint8_t)length;
+    st32(dst, 0, enc);
+    return 7;
+}
+
+/* encode.go:247-282 encodeCopy2 */
+static int encode_copy2(uint8_t *dst, int offset, int length) {
+    length -= 4;
+    offset -= kMinCopy2Offset;
+    st16(dst, 1, (uint16_t)offset);
+    if (length <= 60) {
+        dst[0] = (uint8_t)(length << 2) | TAG_COPY2;
+        return 3;
+    }
+    length -= 60;
+    if (length < 256) {
+        dst[3] = (uint8_t)length;
+        dst[0] = 61 << 2 | TAG_COPY2;
+        return 4;
+    }
+    if (length < 65536) {
+        dst[4] = (uint8_t)(length >> 8);
+        dst[3] = (uint8_t)length;
+        dst[0] = 62 << 2 | TAG_COPY2;
+        return 5;
+    }
+    dst[5] = (uint8_t)(length >> 16);
+    dst[4] = (uint8_t)(length >> 8);
+    dst[3] = (uint8_t)length;
+    dst[0] = 63 << 2 | TAG_COPY2;
+    return 6;
+}
+
+/* asm_none.go:207-278 emitCopy */
+int mzo_emit_copy(uint8_t *dst, int offset, int length) {
+    if (offset > kMaxCopy2Offset) return encode_copy3(dst, offset, length, 0);
+    if (offset <= kMaxCopy1Offset) {
+        offset--;
+        if (length < 15 + 4) {
+            st16(dst, 0, (uint16_t)(offset << 6) | (uint16_t)((length - 4) << 2) | TAG_COPY1);
+            return 2;
+        }
+        if (length < 256 + 18) {
+            st16(dst, 0, (uint16_t)(offset << 6) | (15 << 2 | TAG_COPY1));
+            dst[2] = (uint8_t)(length - 18);
+            return 3;
+        }
+        /* copy1 of 18 bytes, rest as a repeat */
+        st16(dst, 0, (uint16_t)(offset << 6) | (14 << 2) | TAG_COPY1);
+        return 2 + mzo_emit_repeat(dst + 2, length - 18);
+    }
+    return encode_copy2(dst, offset, length);
+}
+
+/* asm_none.go:284-308 emitCopyLits2 */
+int mzo_emit_copy_lits2(uint8_t *dst, const uint8_t *lits, int nlits, int offset, int length) {
+    offset -= kMinCopy2Offset;
+    length -= 4;
+    const int maxraw = kCopy2LitMaxLen - 4;
+    st16(dst, 1, (uint16_t)offset);
+    if (length > maxraw) {
+        dst[0] = TAG_COPY2_FUSED | (uint8_t)(maxraw << 5) | (uint8_t)((nlits - 1) << 3);
+        memcpy(dst + 3, lits, (size_t)nlits);
+        int n = nlits + 3;
+        return n + mzo_emit_repeat(dst + n, length - maxraw);
+    }
+    dst[0] = TAG_COPY2_FUSED | (uint8_t)(length << 5) | (uint8_t)((nlits - 1) << 3);
+    memcpy(dst + 3, lits, (size_t)nlits);
+    return nlits + 3;
+}
+
+/* asm_none.go:313-323 emitCopyLits3 */
+int mzo_emit_copy_lits3(uint8_t *dst, const uint8_t *lits, int nlits, int offset, int length) {
+    int n = encode_copy3(dst, offset, length, nlits);
+    memcpy(dst + n, lits, (size_t)nlits);
+    return n + nlits;
+}
+
+/* ---- match extension helpers ------------------------------------------- */
+
+/* The 8-bytes-at-a-time extension loop "for s <= limit" used by L1
+ * (encode_l1.go:115-122 with limit=sLimit, :181-188/:251-258 with limit=len-8). */
+static inline int extend8(const uint8_t *src, int s, int cand, int limit) {
+    while (s <= limit) {
+        uint64_t diff = ld64(src, s) ^ ld64(src, cand);
+        if (diff != 0) {
+            s += __builtin_ctzll(diff) >> 3;
+            break;
+        }
+        s += 8;
+        cand += 8;
+    }
+    return s;
+}
+
+/* L2 extension with byte tail (encode_l2.go:160-175, :239-254). */
+static inline int extend_tail(const uint8_t *src, int n, int s, int cand) {
+    while (s < n) {
+        if (n - s < 8) {
+            if (src[s] == src[cand]) {
+                s++;
+                cand++;
+                continue;
+            }
+            break;
+        }
+        uint64_t diff = ld64(src, s) ^ ld64(src, cand);
+        if (diff != 0) {
+            s += __builtin_ctzll(diff) >> 3;
+            break;
+        }
+        s += 8;
+        cand += 8;
+    }
+    return s;
+}
+
+/* ---- L1: encode_l1.go:39-283 (tableBits 15, hash6, skipLog 6, fuse<=3) and
+ *          encode_l1.go:285-524 (tableBits 13, hash5, skipLog 5, fuse<=4).
+ * The two Go functions differ only in those parameters, in the width of the
+ * table entries (positions always fit) and in the offset guards, which can
+ * never fire for len <= 64 KiB; one parameterised body restates both. ------ */
+static int64_t encode_l1(uint8_t *dst, const uint8_t *src, int n, int tableBits, int hashBytes,
+                         int skipLog, int maxFuseLits) {
+    uint32_t *table = (uint32_t *)calloc((size_t)1 << tableBits, sizeof(uint32_t)); /* :52 */
+    if (!table) return 0;
+    const int sLimit = n - kInputMargin;       /* :57 */
+    const int dstLimit = n - (n >> 5) - 6;     /* :60 */
+    int nextEmit = 0;                          /* :63 */
+    int s = 1;                                 /* :67 */
+    uint64_t cv = ld64(src, s);                /* :68 */
+    int repeat = 1;                            /* :71 */
+    int d = 0;
+    int candidate;
+
+    for (;;) {
+        candidate = 0;
+        for (;;) {
+            int nextS = s + ((s - nextEmit) >> skipLog) + 4; /* :79 */
+            if (nextS > sLimit) goto emit_remainder;          /* :80-82 */
+            int minSrcPos = s - kMaxCopy3Offset;              /* :83 */
+            uint32_t hash0 = hashN(cv, tableBits, hashBytes);
+            uint32_t hash1 = hashN(cv >> 8, tableBits, hashBytes);
+            candidate = (int)table[hash0];
+            int candidate2 = (int)table[hash1];
+            table[hash0] = (uint32_t)s;
+            table[hash1] = (uint32_t)(s + 1);
+            uint32_t hash2 = hashN(cv >> 16, tableBits, hashBytes); /* :90 */
+
+            /* repeat check at s+1, :94-145 */
+            if ((uint32_t)(cv >> 8) == ld32(src, s - repeat + 1)) {
+                int base = s + 1;
+                for (int i = base - repeat; base > nextEmit && i > 0 && src[i - 1] == src[base - 1];) {
+                    i--;
+                    base--;
+                }
+                if (d + (base - nextEmit) > dstLimit) { /* :103 */
+                    free(table);
+                    return 0;
+                }
+                d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(base - nextEmit));
+                int cand = s - repeat + 4 + 1; /* :113 */
+                s += 4 + 1;
+                s = extend8(src, s, cand, sLimit); /* :115-122 */
+                d += mzo_emit_repeat(dst + d, s - base);
+                nextEmit = s;
+                if (s >= sLimit) goto emit_remainder; /* :139 */
+                cv = ld64(src, s);
+                continue;
+            }
+
+            if (candidate >= minSrcPos && (uint32_t)cv == ld32(src, candidate)) break; /* :147 */
+            candidate = (int)table[hash2];                                               /* :150 */
+            if (candidate2 >= minSrcPos && (uint32_t)(cv >> 8) == ld32(src, candidate2)) {
+                table[hash2] = (uint32_t)(s + 2);
+                candidate = candidate2;
+                s++;
+                break;
+            }
+            table[hash2] = (uint32_t)(s + 2); /* :157 */
+            if (candidate >= minSrcPos && (uint32_t)(cv >> 16) == ld32(src, candidate)) {
+                s += 2;
+                break;
+            }
+            cv = ld64(src, nextS); /* :163 */
+            s = nextS;
+        }
+
+        /* extend backwards, :169-172 */
+        while (candidate > 0 && s > nextEmit && src[candidate - 1] == src[s - 1]) {
+            candidate--;
+            s--;
+        }
+        int base = s;
+        repeat = base - candidate; /* :176 */
+        s += 4;
+        candidate += 4;
+        s = extend8(src, s, candidate, n - 8); /* :181-188 */
+        int length = s - base;
+        if (nextEmit != base) { /* :190-206 */
+            if (base - nextEmit > maxFuseLits || repeat < kMinCopy2Offset) {
+                if (d + (s - nextEmit) > dstLimit) {
+                    free(table);
+                    return 0;
+                }
+                d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(base - nextEmit));
+                d += mzo_emit_copy(dst + d, repeat, length);
+            } else if (repeat <= kMaxCopy2Offset) {
+                d += mzo_emit_copy_lits2(dst + d, src + nextEmit, base - nextEmit, repeat, length);
+            } else {
+                d += mzo_emit_copy_lits3(dst + d, src + nextEmit, base - nextEmit, repeat, length);
+            }
+        } else {
+            d += mzo_emit_copy(dst + d, repeat, length);
+        }
+
+        /* immediate re-match loop, :222-265 */
+        for (;;) {
+            nextEmit = s;
+            if (s >= sLimit) goto emit_remainder;
+            uint64_t x = ld64(src, s - 2);
+            if (d > dstLimit) { /* :229 */
+                free(table);
+                return 0;
+            }
+            uint32_t m2Hash = hashN(x, tableBits, hashBytes);
+            x >>= 16;
+            uint32_t currHash = hashN(x, tableBits, hashBytes);
+            candidate = (int)table[currHash];
+            table[m2Hash] = (uint32_t)(s - 2);
+            table[currHash] = (uint32_t)s;
+            if (s - candidate > kMaxCopy3Offset || (uint32_t)x != ld32(src, candidate)) { /* :242 */
+                cv = ld64(src, s + 1);
+                s++;
+                break;
+            }
+            repeat = s - candidate;
+            base = s;
+            s += 4;
+            candidate += 4;
+            s = extend8(src, s, candidate, n - 8);
+            d += mzo_emit_copy(dst + d, repeat, s - base);
+        }
+    }
+
+emit_remainder: /* :268-282 */
+    free(table);
+    if (nextEmit < n) {
+        if (d + n - nextEmit > dstLimit) return 0;
+        d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(n - nextEmit));
+    }
+    return d;
+}
+
+/* asm_none.go:51-59 encodeBlock */
+int64_t mzo_encode_block_l1(uint8_t *dst, const uint8_t *src, size_t n) {
+    if (n < kMinNonLiteralBlockSize || n > MZO_MAX_BLOCK_SIZE) return 0;
+    if (n <= 65536) return encode_l1(dst, src, (int)n, 13, 5, 5, kMaxCopy2Lits);
+    return encode_l1(dst, src, (int)n, 15, 6, 6, kMaxCopy3Lits);
+}
+
+/* ---- L2: encode_l2.go:61-338 (long 17 bit hash7 / short 14 bit hash4) and
+ *          encode_l2.go:343-596 (long 15 bit hash6 / short 12 bit hash4).
+ * As for L1, one parameterised body: the 64K variant drops guards that cannot
+ * fire for len <= 64 KiB (minSrcPos, the far-4-byte-match bail, copy3). ----- */
+static int64_t encode_l2(uint8_t *dst, const uint8_t *src, int n, int lBits, int lHashBytes, int sBits) {
+    const int sLimit = n - kInputMargin; /* :65 */
+    uint32_t *lTable = (uint32_t *)calloc(((size_t)1 << lBits) + ((size_t)1 << sBits), sizeof(uint32_t));
+    if (!lTable) return 0;
+    uint32_t *sTable = lTable + ((size_t)1 << lBits);
+    const int dstLimit = n - (n >> 5) - 6; /* :92 */
+    int nextEmit = 0;
+    int s = 1;
+    uint64_t cv = ld64(src, s);
+    int repeat = 1; /* :102 */
+    int d = 0;
+
+#define LHASH(v) hashN((v), lBits, lHashBytes)
+#define SHASH(v) hash4((v), sBits)
+
+    for (;;) {
+        int candidateL = 0;
+        int nextS = 0;
+        for (;;) {
+            nextS = s + ((s - nextEmit) >> 7) + 1; /* :114 */
+            if (nextS > sLimit) goto emit_remainder;
+            int minSrcPos = s - kMaxCopy3Offset + 1; /* :118 */
+            uint32_t hashL = LHASH(cv);
+            uint32_t hashS = SHASH(cv);
+            candidateL = (int)lTable[hashL];
+            int candidateS = (int)sTable[hashS];
+            lTable[hashL] = (uint32_t)s;
+            sTable[hashS] = (uint32_t)s;
+
+            uint64_t valLong = ld64(src, candidateL);
+            uint64_t valShort = ld64(src, candidateS);
+
+            if (candidateL > minSrcPos && cv == valLong) break; /* :130 */
+
+            /* repeat at s+1, 4 bytes: :134-196 */
+            const uint64_t repeatMask = 0xffffffffull << 8;
+            if (repeat > 0 && (cv & repeatMask) == (ld64(src, s - repeat) & repeatMask)) {
+                int base = s + 1;
+                for (int i = base - repeat; base > nextEmit && i > 0 && src[i - 1] == src[base - 1];) {
+                    i--;
+                    base--;
+                }
+                if (d + (base - nextEmit) > dstLimit) { /* :147 */
+                    free(lTable);
+                    return 0;
+                }
+                d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(base - nextEmit));
+                int cand = s - repeat + 4 + 1;
+                s += 4 + 1;
+                s = extend_tail(src, n, s, cand); /* :160-175 */
+                d += mzo_emit_repeat(dst + d, s - base);
+                nextEmit = s;
+                if (s >= sLimit) goto emit_remainder; /* :179 */
+                int index0 = base + 1;
+                int index1 = s - 2;
+                while (index0 < index1) { /* :186-195 */
+                    uint64_t cv0 = ld64(src, index0);
+                    uint64_t cv1 = ld64(src, index1);
+                    lTable[LHASH(cv0)] = (uint32_t)index0;
+                    sTable[SHASH(cv0 >> 8)] = (uint32_t)(index0 + 1);
+                    lTable[LHASH(cv1)] = (uint32_t)index1;
+                    sTable[SHASH(cv1 >> 8)] = (uint32_t)(index1 + 1);
+                    index0 += 2;
+                    index1 -= 2;
+                }
+                cv = ld64(src, s);
+                continue;
+            }
+
+            if (candidateL >= minSrcPos && (uint32_t)cv == (uint32_t)valLong) break; /* :199 */
+
+            if (candidateS >= minSrcPos && (uint32_t)cv == (uint32_t)valShort) { /* :204 */
+                hashL = LHASH(cv >> 8);
+                candidateL = (int)lTable[hashL];
+                lTable[hashL] = (uint32_t)(s + 1);
+                if (candidateL > minSrcPos && (uint32_t)(cv >> 8) == ld32(src, candidateL)) {
+                    s++;
+                    break;
+                }
+                candidateL = candidateS;
+                break;
+            }
+            cv = ld64(src, nextS); /* :218 */
+            s = nextS;
+        }
+
+        /* extend backwards, :223-226 */
+        while (candidateL > 0 && s > nextEmit && src[candidateL - 1] == src[s - 1]) {
+            candidateL--;
+            s--;
+        }
+        if (d + (s - nextEmit) > dstLimit) { /* :229 */
+            free(lTable);
+            return 0;
+        }
+        int base = s;
+        int offset = base - candidateL;
+        s += 4;
+        candidateL += 4;
+        s = extend_tail(src, n, s, candidateL); /* :239-254 */
+
+        /* :257-264 drop far 4-byte matches */
+        if (offset > 65535 && s - base <= 4 && repeat != offset) {
+            s = nextS + 1;
+            if (s >= sLimit) goto emit_remainder;
+            cv = ld64(src, s);
+            continue;
+        }
+
+        int nlits = base - nextEmit; /* :266-289 */
+        if (nlits > 0) {
+            if (offset <= kMaxCopy2Offset) {
+                if (nlits > kMaxCopy2Lits || offset < 64) {
+                    d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)nlits);
+                    d += mzo_emit_copy(dst + d, offset, s - base);
+                } else {
+                    d += mzo_emit_copy_lits2(dst + d, src + nextEmit, nlits, offset, s - base);
+                }
+            } else {
+                if (nlits > kMaxCopy3Lits) {
+                    d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)nlits);
+                    d += mzo_emit_copy(dst + d, offset, s - base);
+                } else {
+                    d += mzo_emit_copy_lits3(dst + d, src + nextEmit, nlits, offset, s - base);
+                }
+            }
+        } else {
+            d += mzo_emit_copy(dst + d, offset, s - base);
+        }
+        repeat = offset;
+        nextEmit = s;
+        if (s >= sLimit) goto emit_remainder; /* :293 */
+        if (d > dstLimit) {                   /* :297 */
+            free(lTable);
+            return 0;
+        }
+
+        /* index short & long, :303-326 */
+        int index0 = base + 1;
+        int index1 = s - 2;
+        uint64_t cv0 = ld64(src, index0);
+        uint64_t cv1 = ld64(src, index1);
+        lTable[LHASH(cv0)] = (uint32_t)index0;
+        sTable[SHASH(cv0 >> 8)] = (uint32_t)(index0 + 1);
+        lTable[LHASH(cv1)] = (uint32_t)index1;
+        sTable[SHASH(cv1 >> 8)] = (uint32_t)(index1 + 1);
+        index0 += 1;
+        index1 -= 1;
+        cv = ld64(src, s);
+        int index2 = (index0 + index1 + 1) >> 1;
+        while (index2 < index1) {
+            lTable[LHASH(ld64(src, index0))] = (uint32_t)index0;
+            lTable[LHASH(ld64(src, index2))] = (uint32_t)index2;
+            index0 += 2;
+            index2 += 2;
+        }
+    }
+
+emit_remainder: /* :329-337 */
+    free(lTable);
+    if (nextEmit < n) {
+        if (d + n - nextEmit > dstLimit) return 0;
+        d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(n - nextEmit));
+    }
+    return d;
+#undef LHASH
+#undef SHASH
+}
+
+/* asm_none.go:68-76 encodeBlockBetter */
+int64_t mzo_encode_block_l2(uint8_t *dst, const uint8_t *src, size_t n) {
+    if (n < kMinNonLiteralBlockSize || n > MZO_MAX_BLOCK_SIZE) return 0;
+    if (n <= (64 << 10)) return encode_l2(dst, src, (int)n, 15, 6, 12);
+    return encode_l2(dst, src, (int)n, 17, 7, 14);
+}
+
+/* ---- decoder: decode.go:178-622 ---------------------------------------
+ * One bounds-checked loop.  The Go function has a fast loop (src slack >= 11)
+ * and a checked tail loop; they accept/reject identically and write identical
+ * bytes on success (the fast loop's 4-byte fused-literal store :313-320 is
+ * always overwritten by the >=4-byte copy that follows), so the checked tail
+ * loop :362-611 is restated for every token. */
+int mzo_decode_block(uint8_t *dst, size_t dst_len_, const uint8_t *src, size_t src_len_) {
+    const int64_t dlen = (int64_t)dst_len_, slen = (int64_t)src_len_;
+    int64_t d = 0, s = 0, length = 0;
+    int64_t offset = 1; /* :186 */
+
+    while (s < slen) {
+        uint8_t tag = src[s];
+        switch (tag & 3) {
+        case 0: { /* literal / repeat :367-423 */
+            uint32_t x = tag >> 3;
+            if (x < 29) {
+                s++;
+                length = x + 1;
+            } else if (x == 29) {
+                s += 2;
+                if (s > slen) return 1;
+                length = (int64_t)src[s - 1] + 30;
+            } else if (x == 30) {
+                s += 3;
+                if (s > slen) return 1;
+                length = (int64_t)(src[s - 2] | (uint32_t)src[s - 1] << 8) + 30;
+            } else {
+                s += 4;
+                if (s > slen) return 1;
+                length = (int64_t)(src[s - 3] | (uint32_t)src[s - 2] << 8 | (uint32_t)src[s - 1] << 16) + 30;
+            }
+            if (tag & 4) break; /* repeat: goto doCopy2 */
+            if (length > dlen - d || length > slen - s) return 1; /* :410 */
+            memcpy(dst + d, src + s, (size_t)length);
+            d += length;
+            s += length;
+            continue;
+        }
+        case 1: /* copy1 :425-448 */
+            s += 2;
+            if (s > slen) return 1;
+            length = (src[s - 2] >> 2) & 15;
+            offset = (int64_t)(ld16(src, s - 2) >> 6) + 1;
+            if (length == 15) {
+                s++;
+                if (s > slen) return 1;
+                length = (int64_t)src[s - 1] + 18;
+            } else {
+                length += 4;
+            }
+            break;
+        case 2: /* copy2 :449-495 */
+            s += 3;
+            if (s > slen) return 1;
+            length = src[s - 3] >> 2;
+            offset = (int64_t)(src[s - 2] | (uint32_t)src[s - 1] << 8);
+            if (length <= 60) {
+                length += 4;
+            } else if (length == 61) {
+                s++;
+                if (s > slen) return 1;
+                length = (int64_t)src[s - 1] + 64;
+            } else if (length == 62) {
+                s += 2;
+                if (s > slen) return 1;
+                length = (int64_t)(src[s - 2] | (uint32_t)src[s - 1] << 8) + 64;
+            } else {
+                s += 3;
+                if (s > slen) return 1;
+                length = (int64_t)(src[s - 3] | (uint32_t)src[s - 2] << 8 | (uint32_t)src[s - 1] << 16) + 64;
+            }
+            offset += kMinCopy2Offset;
+            break;
+        default: { /* fused copy2 / copy3 :496-569 */
+            s += 4;
+            if (s > slen) return 1;
+            uint32_t val = ld32(src, s - 4);
+            int isCopy3 = (val & 4) != 0;
+            int64_t litLen = (val >> 3) & 3;
+            if (!isCopy3) {
+                length = 4 + ((val >> 5) & 7);
+                offset = (int64_t)((val >> 8) & 65535) + kMinCopy2Offset;
+                s--;
+                litLen++;
+            } else {
+                uint32_t lengthTmp = (val >> 5) & 63;
+                offset = (int64_t)(val >> 11) + kMinCopy3Offset;
+                if (lengthTmp >= 61) {
+                    if (lengthTmp == 61) {
+                        s++;
+                        if (s > slen) return 1;
+                        length = (int64_t)src[s - 1] + 64;
+                    } else if (lengthTmp == 62) {
+                        s += 2;
+                        if (s > slen) return 1;
+                        length = (int64_t)(src[s - 2] | (uint32_t)src[s - 1] << 8) + 64;
+                    } else {
+                        s += 3;
+                        if (s > slen) return 1;
+                        length = (int64_t)(src[s - 3] | (uint32_t)src[s - 2] << 8 | (uint32_t)src[s - 1] << 16) + 64;
+                    }
+                } else {
+                    length = lengthTmp + 4;
+                }
+            }
+            if (litLen > 0) { /* :556-568 */
+                if (litLen > dlen - d || s + litLen > slen) return 1;
+                memcpy(dst + d, src + s, (size_t)litLen);
+                d += litLen;
+                s += litLen;
+            }
+            break;
+        }
+        }
+        /* doCopy2 :572-610 */
+        if (offset <= 0 || d < offset || length > dlen - d) return 1;
+        if (offset > length) {
+            memcpy(dst + d, dst + d - offset, (size_t)length);
+        } else {
+            uint8_t *a = dst + d;
+            const uint8_t *b = dst + d - offset;
+            for (int64_t i = 0; i < length; i++) a[i] = b[i];
+        }
+        d += length;
+    }
+    if (d != dlen) return 1; /* :615 */
+    return 0;
+}
+
+/* ---- wrappers ---------------------------------------------------------- */
+
+/* encoding/binary PutUvarint */
+static int put_uvarint(uint8_t *dst, uint64_t x) {
+    int i = 0;
+    while (x >= 0x80) {
+        dst[i++] = (uint8_t)x | 0x80;
+        x >>= 7;
+    }
+    dst[i] = (uint8_t)x;
+    return i + 1;
+}
+
+/* encoding/binary Uvarint: n>0 ok, 0 short buffer, <0 overflow */
+static int get_uvarint(const uint8_t *buf, size_t len, uint64_t *out) {
+    uint64_t x = 0;
+    unsigned sft = 0;
+    for (size_t i = 0; i < len; i++) {
+        uint8_t b = buf[i];
+        if (i == 10) return -(int)(i + 1);
+        if (b < 0x80) {
+            if (i == 9 && b > 1) return -(int)(i + 1);
+            *out = x | (uint64_t)b << sft;
+            return (int)i + 1;
+        }
+        x |= (uint64_t)(b & 0x7f) << sft;
+        sft += 7;
+    }
+    *out = 0;
+    return 0;
+}
+
+/* encode.go:223-229 encodeUncompressed */
+static int64_t encode_uncompressed(uint8_t *dst, size_t cap, const uint8_t *src, size_t n) {
+    if (n == 0) {
+        if (cap < 1) return MZO_ERR_DST_TOO_SMALL;
+        dst[0] = 0;
+        return 1;
+    }
+    if (cap < n + 2) return MZO_ERR_DST_TOO_SMALL;
+    dst[0] = 0;
+    dst[1] = 0;
+    memcpy(dst + 2, src, n);
+    return (int64_t)n + 2;
+}
+
+/* encode.go:74-139 Encode */
+int64_t mzo_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, int level) {
+    int64_t maxlen = mzo_max_encoded_len((int64_t)n);
+    if (maxlen < 0) return MZO_ERR_TOO_LARGE;
+    if (n < kMinNonLiteralBlockSize) return encode_uncompressed(dst, dst_cap, src, n);
+    /* Go allocates MaxEncodedLen when dst is short; a C caller must provide it.
+     * The block encoders need headroom beyond n+2 while probing, as in Go
+     * (dst[d:] where len(dst)=n+2, bails keep d below dstLimit). */
+    if ((int64_t)dst_cap < maxlen) return MZO_ERR_DST_TOO_SMALL;
+    if (level != 0 && level != 1 && level != 2) return MZO_ERR_INVALID_LEVEL;
+    if (level == 0) return encode_uncompressed(dst, dst_cap, src, n);
+    dst[0] = 0;
+    int d = 1 + put_uvarint(dst + 1, n);
+    /* The Go encoders may transiently write up to a few bytes past n+2-d while
+     * emitting the token that trips the dstLimit bail; encode into a scratch
+     * buffer with slack so the oracle never depends on that. */
+    uint8_t *tmp = (uint8_t *)malloc(n + 64);
+    if (!tmp) return MZO_ERR_DST_TOO_SMALL;
+    int64_t m = level == 1 ? mzo_encode_block_l1(tmp, src, n) : mzo_encode_block_l2(tmp, src, n);
+    if (m > 0) {
+        memcpy(dst + d, tmp, (size_t)m);
+        free(tmp);
+        return d + m;
+    }
+    free(tmp);
+    return encode_uncompressed(dst, dst_cap, src, n);
+}
+
+/* encode.go:168-207 TryEncode */
+int64_t mzo_try_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, int level) {
+    int64_t maxlen = mzo_max_encoded_len((int64_t)n);
+    if (maxlen < 0 || (int64_t)dst_cap < maxlen) return 0;
+    if (n < kMinNonLiteralBlockSize) return 0;
+    if (level != 1 && level != 2) return 0;
+    dst[0] = 0;
+    int d = 1 + put_uvarint(dst + 1, n);
+    uint8_t *tmp = (uint8_t *)malloc(n + 64);
+    if (!tmp) return 0;
+    int64_t m = level == 1 ? mzo_encode_block_l1(tmp, src, n) : mzo_encode_block_l2(tmp, src, n);
+    if (m > 0 && d + m < (int64_t)n) {
+        memcpy(dst + d, tmp, (size_t)m);
+        free(tmp);
+        return d + m;
+    }
+    free(tmp);
+    return 0;
+}
+
+/* decode.go:160-171 decodedLen */
+static int decoded_len_hdr(const uint8_t *src, size_t n, int64_t *v, int *hdr) {
+    uint64_t x;
+    int k = get_uvarint(src, n, &x);
+    if (k <= 0 || x > 0xffffffffull) return MZO_ERR_CORRUPT;
+    *v = (int64_t)x;
+    *hdr = k;
+    return MZO_OK;
+}
+
+/* decode.go:120-156 isMinLZ */
+int mzo_is_minlz(const uint8_t *src, size_t n, int *is_mlz, int *lits, size_t *hdr, int64_t *size) {
+    *is_mlz = 0;
+    *lits = 0;
+    *hdr = 0;
+    *size = 0;
+    if (n <= 1) {
+        if (n == 0) return MZO_ERR_CORRUPT;
+        if (src[0] == 0) {
+            *is_mlz = 1;
+            *lits = 1;
+            *hdr = 1;
+            return MZO_OK;
+        }
+    }
+    if (src[0] != 0) {
+        int64_t v;
+        int h;
+        int e = decoded_len_hdr(src, n, &v, &h);
+        if (e) return e;
+        *size = v;
+        return MZO_OK; /* not MinLZ: Snappy/S2 territory */
+    }
+    int64_t v;
+    int h;
+    int e = decoded_len_hdr(src + 1, n - 1, &v, &h);
+    if (e) return e;
+    if (v > MZO_MAX_BLOCK_SIZE) return MZO_ERR_TOO_LARGE;
+    size_t rest = n - 1 - (size_t)h;
+    if (rest == 0) return MZO_ERR_CORRUPT;
+    *hdr = 1 + (size_t)h;
+    if (v == 0) {
+        *is_mlz = 1;
+        *lits = 1;
+        *size = (int64_t)rest;
+        return MZO_OK;
+    }
+    if (v < (int64_t)rest) {
+        *size = v;
+        return MZO_ERR_CORRUPT;
+    }
+    *is_mlz = 1;
+    *size = v;
+    return MZO_OK;
+}
+
+/* decode.go:107-111 DecodedLen */
+int64_t mzo_decoded_len(const uint8_t *src, size_t n) {
+    int a, b;
+    size_t h;
+    int64_t v;
+    int e = mzo_is_minlz(src, n, &a, &b, &h, &v);
+    return e ? e : v;
+}
+
+/* decode.go:50-78 Decode (MinLZ blocks only; first byte != 0 is the S2/Snappy
+ * fallback, which lives in host Go and is outside this path). */
+int64_t mzo_decode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n) {
+    int is_mlz, lits;
+    size_t hdr;
+    int64_t size;
+    int e = mzo_is_minlz(src, n, &is_mlz, &lits, &hdr, &size);
+    if (e) return e;
+    if (lits) {
+        if ((size_t)size > dst_cap) return MZO_ERR_DST_TOO_SMALL;
+        memcpy(dst, src + hdr, (size_t)size);
+        return size;
+    }
+    if (!is_mlz) return MZO_ERR_UNSUPPORTED;
+    if ((size_t)size > dst_cap) return MZO_ERR_DST_TOO_SMALL;
+    if (mzo_decode_block(dst, (size_t)size, src + hdr, n - hdr) != 0) return MZO_ERR_CORRUPT;
+    return size;
+}
+
+/* ---- CRC32C: minlz.go:133-140 ------------------------------------------ */
+static uint32_t crc_tab[8][256];
+static pthread_once_t crc_once = PTHREAD_ONCE_INIT;
+static void crc_init(void) {
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x82f63b78u : c >> 1;
+        crc_tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; i++)
+        for (int t = 1; t < 8; t++) crc_tab[t][i] = (crc_tab[t - 1][i] >> 8) ^ crc_tab[0][crc_tab[t - 1][i] & 0xff];
+}
+
+uint32_t mzo_crc(const uint8_t *b, size_t n) {
+    pthread_once(&crc_once, crc_init);
+    uint32_t c = 0xffffffffu;
+    while (n >= 8) {
+        uint64_t v = ld64(b, 0) ^ c;
+        c = crc_tab[7][v & 0xff] ^ crc_tab[6][(v >> 8) & 0xff] ^ crc_tab[5][(v >> 16) & 0xff] ^
+            crc_tab[4][(v >> 24) & 0xff] ^ crc_tab[3][(v >> 32) & 0xff] ^ crc_tab[2][(v >> 40) & 0xff] ^
+            crc_tab[1][(v >> 48) & 0xff] ^ crc_tab[0][v >> 56];
+        b += 8;
+        n -= 8;
+    }
+    while (n--) c = crc_tab[0][(c ^ *b++) & 0xff] ^ (c >> 8);
+    c = ~c;
+    return (c >> 15 | c << 17) + 0xa282ead8u;
+}
+
+/* ---- multi-threaded batch drivers (CPU baseline leg) ------------------- */
+typedef struct {
+    int level, nblk;
+    const uint8_t *src;
+    const uint64_t *src_off;
+    uint8_t *dst;
+    const uint64_t *dst_off;
+    uint32_t *out_len;
+    int32_t *status;
+    volatile int next;
+    int decode;
+} batch_job;
+
+static void *batch_worker(void *arg) {
+    batch_job *j = (batch_job *)arg;
+    for (;;) {
+        int i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->nblk) break;
+        const uint8_t *s = j->src + j->src_off[i];
+        size_t sn = (size_t)(j->src_off[i + 1] - j->src_off[i]);
+        uint8_t *d = j->dst + j->dst_off[i];
+        size_t dn = (size_t)(j->dst_off[i + 1] - j->dst_off[i]);
+        if (j->decode) {
+            j->status[i] = mzo_decode_block(d, dn, s, sn);
+        } else {
+            int64_t m = j->level == 1 ? mzo_encode_block_l1(d, s, sn) : mzo_encode_block_l2(d, s, sn);
+            j->out_len[i] = (uint32_t)m;
+        }
+    }
+    return NULL;
+}
+
+static int run_batch(batch_job *j, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    j->next = 0;
+    for (int t = 1; t < nthreads; t++)
+        if (pthread_create(&th[t], NULL, batch_worker, j)) return -1;
+    batch_worker(j);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+    return 0;
+}
+
+int mzo_encode_batch_mt(int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                        const uint64_t *dst_off, uint32_t *out_len, int nthreads) {
+    if (level != 1 && level != 2) return MZO_ERR_INVALID_LEVEL;
+    batch_job j = {level, nblk, src, src_off, dst, dst_off, out_len, NULL, 0, 0};
+    return run_batch(&j, nthreads);
+}
+
+int mzo_decode_batch_mt(int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                        const uint64_t *dst_off, int32_t *status, int nthreads) {
+    batch_job j = {0, nblk, src, src_off, dst, dst_off, NULL, status, 0, 1};
+    return run_batch(&j, nthreads);
+}
