@@ -1,0 +1,140 @@
+/*
+ * minlz_cuda.h -- C ABI of libminlz_cuda.so: the MinLZ block encode / decode
+ * hot path as hand-written sm_100a CUDA kernels, batch-first.
+ *
+ * This is the drop-in boundary for the per-architecture seam of minio/minlz
+ * (the functions that build tags select between asm_amd64.s and the pure-Go
+ * path).  Each entry point names the reference interface it replaces; paths
+ * are relative to the reference tree.  INTEGRATION.md shows the cgo binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types; thread-safe and re-entrant
+ *     (any goroutine / OS thread); the library owns no caller memory.
+ *   - a batch is a flat byte buffer plus an offset table of nblk+1 uint64
+ *     (block i = [off[i], off[i+1])).  Flat + offsets rather than pointer
+ *     arrays because cgo may not pass Go memory holding Go pointers.
+ *   - "blocks" entry points work at the reference's internal seam: token
+ *     streams WITHOUT the 0x00 + uvarint(len) block header
+ *     (encode_amd64.go:111-118, decode_amd64.go:21).
+ *   - return value 0 = ok, negative = MZCU_ERR_*; per-block results go to
+ *     out_len[] / status[] exactly as the reference's int returns.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with MZCU_ERR_CUDA.
+ */
+#ifndef MINLZ_CUDA_H
+#define MINLZ_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZCU_ABI_VERSION 1
+
+/* minlz.go:24 MaxBlockSize */
+#define MZCU_MAX_BLOCK_SIZE (8 << 20)
+
+/* encode.go:20-42 levels (only the levels on the hot path are accepted) */
+#define MZCU_LEVEL_UNCOMPRESSED 0
+#define MZCU_LEVEL_FASTEST 1  /* encode_l1.go  encodeBlock        */
+#define MZCU_LEVEL_BALANCED 2 /* encode_l2.go  encodeBlockBetter  */
+
+/* decode.go:29-40 error values */
+#define MZCU_OK 0
+#define MZCU_ERR_CORRUPT (-1)       /* ErrCorrupt      */
+#define MZCU_ERR_TOO_LARGE (-2)     /* ErrTooLarge     */
+#define MZCU_ERR_UNSUPPORTED (-3)   /* first byte != 0: Snappy/S2 fallback stays in host Go (decode.go:59-68) */
+#define MZCU_ERR_INVALID_LEVEL (-4) /* ErrInvalidLevel */
+#define MZCU_ERR_DST_TOO_SMALL (-5) /* C callers must size dst; Go would allocate */
+#define MZCU_ERR_CUDA (-6)          /* CUDA runtime failure / no device; see mzcu_last_error */
+#define MZCU_ERR_INVALID_ARG (-7)
+
+/* decode.go:25-27 decodeErrCodeCorrupt: per-block status of the decode seam */
+#define MZCU_BLOCK_OK 0
+#define MZCU_BLOCK_CORRUPT 1
+
+int mzcu_abi_version(void);
+/* Thread-local message of the last failing call on this thread. */
+const char *mzcu_last_error(void);
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int mzcu_device_count(void);
+
+/* ---- pure helpers (no device work) ------------------------------------ */
+
+/* encode.go:234-244 MaxEncodedLen: n+2, 1 for n==0, -1 for n > 8 MiB. */
+int64_t mzcu_max_encoded_len(int64_t src_len);
+/* decode.go:107 DecodedLen / decode.go:120 isMinLZ on a full block.
+ * Returns the decoded length or MZCU_ERR_*. */
+int64_t mzcu_decoded_len(const uint8_t *block, size_t n);
+/* decode.go:114 IsMinLZ: *is_minlz=1 when the block is MinLZ (first byte 0),
+ * *size = decoded size.  Returns MZCU_OK or MZCU_ERR_*. */
+int mzcu_is_minlz(const uint8_t *block, size_t n, int *is_minlz, int64_t *size);
+
+/* ---- seam level, device pointers (what the benchmarks time) ------------
+ *
+ * replaces: encodeBlock / encodeBlockBetter (encode_amd64.go:119,201;
+ *           asm_none.go:51,68) applied to every block of a batch.
+ *   src/src_off : device; uncompressed blocks, 16 <= len <= 8 MiB each
+ *                 (shorter blocks yield out_len 0, as the reference).
+ *   dst/dst_off : device; per-block capacity >= MaxEncodedLen(len).
+ *   out_len     : device uint32[nblk]; bytes written, 0 = not compressible
+ *                 (caller stores the block raw, encode.go:137-138).
+ *   stream      : cudaStream_t (as void*); the call is asynchronous.
+ */
+int mzcu_encode_blocks_dev(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
+                           uint8_t *dst, const uint64_t *dst_off, uint32_t *out_len, void *stream);
+
+/* replaces: minLZDecode (decode_amd64.go:21 / decode_other.go:23 /
+ *           decode.go:178) applied to every block of a batch.
+ *   src/src_off : device; token streams.
+ *   dst/dst_off : device; dst_off[i+1]-dst_off[i] must equal the decoded
+ *                 length of block i (len(dst) in the reference).
+ *   status      : device int32[nblk]; 0 ok / 1 corrupt.  A corrupt block
+ *                 never writes outside its own dst range.
+ */
+int mzcu_decode_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                           const uint64_t *dst_off, int32_t *status, void *stream);
+
+/* ---- seam level, host pointers (synchronous; H2D + kernel + D2H) -------
+ * Same contracts with host memory; pinned memory (mzcu_host_alloc) makes the
+ * copies asynchronous-capable and ~2x faster.  device < 0 = current device. */
+int mzcu_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                       const uint64_t *dst_off, uint32_t *out_len);
+int mzcu_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                       const uint64_t *dst_off, int32_t *status);
+
+/* ---- block API level (full blocks with header), host pointers ----------
+ *
+ * replaces: Encode (encode.go:74-139).  Writes 0x00 + uvarint(len) + tokens,
+ * or the stored form 00 00 raw when len < 16 / level 0 / incompressible.
+ * dst_cap must be >= mzcu_max_encoded_len(n).  Returns the encoded length. */
+int64_t mzcu_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, int level);
+/* replaces: TryEncode (encode.go:168-207): 0 when Go returns nil. */
+int64_t mzcu_try_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, int level);
+/* replaces: Decode (decode.go:50-78) for MinLZ blocks.  Returns the decoded
+ * length; on MZCU_ERR_CORRUPT dst holds the partial output like Go's
+ * `return dst, ErrCorrupt`. */
+int64_t mzcu_decode(uint8_t *dst, size_t dst_cap, const uint8_t *block, size_t n);
+
+/* Batch forms of Encode / Decode over full blocks (header included in dst /
+ * src).  enc_len[i] receives the encoded size of block i (always > 0),
+ * dec_len[i] the decoded size or a negative MZCU_ERR_*. */
+int mzcu_encode_batch(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                      const uint64_t *dst_off, uint64_t *enc_len);
+int mzcu_decode_batch(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                      const uint64_t *dst_off, int64_t *dec_len);
+
+/* ---- pinned host memory for callers that want fast H2D / D2H ---------- */
+void *mzcu_host_alloc(size_t n);
+void mzcu_host_free(void *p);
+
+/* Last kernel duration in milliseconds measured with CUDA events around the
+ * kernels of the most recent host-pointer call on this thread (0 if none). */
+float mzcu_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINLZ_CUDA_H */

@@ -1,0 +1,615 @@
+// mz_api.cu -- C ABI of libminlz_cuda.so (see include/minlz_cuda.h).
+//
+// Host side of the drop-in boundary: argument checking, block-header handling
+// (reference encode.go:74-139, decode.go:50-171), device workspace pooling,
+// launches.  All compression / decompression work happens in the CUDA kernels;
+// there is no CPU codec in this library.
+#include "../../include/minlz_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "mz_decode.cuh"
+#include "mz_encode_l1.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local float g_last_kernel_ms = 0.f;
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) return fail(MZCU_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- per-device state ------------------------------------------------------
+constexpr int kMaxDevices = 64;
+constexpr int kCounterSlots = 1024;
+
+struct DeviceState {
+    std::once_flag once;
+    cudaError_t init_err = cudaSuccess;
+    int num_sms = 0;
+    int *counters = nullptr;  // kCounterSlots ints
+    std::atomic<unsigned> next_counter{0};
+};
+DeviceState g_dev[kMaxDevices];
+
+int resolve_device(int device) {
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return -1;
+    }
+    return (device >= 0 && device < kMaxDevices) ? device : -1;
+}
+
+int init_device(int device) {
+    DeviceState &st = g_dev[device];
+    std::call_once(st.once, [&] {
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) e = cudaMalloc(&st.counters, kCounterSlots * sizeof(int));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mz::encode_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+        st.init_err = e;
+    });
+    if (st.init_err != cudaSuccess)
+        return fail(MZCU_ERR_CUDA, "device %d init: %s", device, cudaGetErrorString(st.init_err));
+    CU_TRY(cudaSetDevice(device));
+    return MZCU_OK;
+}
+
+// ---- launches --------------------------------------------------------------
+int launch_decode(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint8_t *dst,
+                  const uint64_t *dbeg, const uint64_t *dend, int32_t *status, cudaStream_t stream) {
+    (void)device;
+    if (nblk == 0) return MZCU_OK;
+    constexpr int kWarps = 4;
+    int grid = (nblk + kWarps - 1) / kWarps;
+    mz::decode_warp_serial_kernel<kWarps><<<grid, kWarps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, dend, status);
+    CU_TRY(cudaGetLastError());
+    return MZCU_OK;
+}
+
+int launch_encode(int device, int level, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send,
+                  uint8_t *dst, const uint64_t *dbeg, uint32_t *out_len, cudaStream_t stream) {
+    if (nblk == 0) return MZCU_OK;
+    DeviceState &st = g_dev[device];
+    int *counter = st.counters + (st.next_counter.fetch_add(1) % kCounterSlots);
+    CU_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    if (level == MZCU_LEVEL_FASTEST) {
+        int grid = nblk < st.num_sms ? nblk : st.num_sms;
+        mz::encode_l1_kernel<<<grid, 32, 128 << 10, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len, counter);
+    } else {
+        return fail(MZCU_ERR_INVALID_LEVEL, "level %d not implemented on device", level);
+    }
+    CU_TRY(cudaGetLastError());
+    return MZCU_OK;
+}
+
+// ---- pooled host-call workspaces ------------------------------------------
+struct Workspace {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    size_t cap_src = 0, cap_dst = 0;
+    uint64_t *d_tab = nullptr;  // 4 offset arrays + out/status
+    size_t cap_tab = 0;         // in blocks
+    uint64_t *h_tab = nullptr;  // pinned mirror of d_tab
+};
+
+std::mutex g_ws_mu;
+std::vector<Workspace *> g_ws_free;
+
+int ws_acquire(int device, Workspace **out) {
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        for (size_t i = 0; i < g_ws_free.size(); i++) {
+            if (g_ws_free[i]->device == device) {
+                *out = g_ws_free[i];
+                g_ws_free.erase(g_ws_free.begin() + i);
+                return MZCU_OK;
+            }
+        }
+    }
+    Workspace *w = new Workspace();
+    w->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
+    if (e != cudaSuccess) {
+        delete w;
+        return fail(MZCU_ERR_CUDA, "workspace: %s", cudaGetErrorString(e));
+    }
+    *out = w;
+    return MZCU_OK;
+}
+
+void ws_release(Workspace *w) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    g_ws_free.push_back(w);
+}
+
+int ws_reserve(Workspace *w, size_t src_bytes, size_t dst_bytes, size_t nblk) {
+    auto grow = [](uint8_t **p, size_t *cap, size_t need) -> cudaError_t {
+        if (need <= *cap) return cudaSuccess;
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+        size_t want = need + need / 4 + 256;
+        cudaError_t e = cudaMalloc(p, want);
+        if (e == cudaSuccess) *cap = want;
+        return e;
+    };
+    CU_TRY(grow(&w->d_src, &w->cap_src, src_bytes + 64));
+    CU_TRY(grow(&w->d_dst, &w->cap_dst, dst_bytes + 64));
+    if (nblk + 1 > w->cap_tab) {
+        if (w->d_tab) cudaFree(w->d_tab);
+        if (w->h_tab) cudaFreeHost(w->h_tab);
+        w->d_tab = nullptr;
+        w->h_tab = nullptr;
+        w->cap_tab = 0;
+        size_t want = (nblk + 1) * 2;
+        CU_TRY(cudaMalloc(&w->d_tab, want * 5 * sizeof(uint64_t)));
+        CU_TRY(cudaMallocHost(&w->h_tab, want * 5 * sizeof(uint64_t)));
+        w->cap_tab = want;
+    }
+    return MZCU_OK;
+}
+
+struct WsGuard {
+    Workspace *w = nullptr;
+    ~WsGuard() {
+        if (w) ws_release(w);
+    }
+};
+
+// uvarint helpers (encoding/binary semantics)
+int put_uvarint(uint8_t *dst, uint64_t x) {
+    int i = 0;
+    while (x >= 0x80) {
+        dst[i++] = (uint8_t)x | 0x80;
+        x >>= 7;
+    }
+    dst[i] = (uint8_t)x;
+    return i + 1;
+}
+
+int get_uvarint(const uint8_t *buf, size_t len, uint64_t *out) {
+    uint64_t x = 0;
+    unsigned sft = 0;
+    for (size_t i = 0; i < len; i++) {
+        uint8_t b = buf[i];
+        if (i == 10) return -(int)(i + 1);
+        if (b < 0x80) {
+            if (i == 9 && b > 1) return -(int)(i + 1);
+            *out = x | (uint64_t)b << sft;
+            return (int)i + 1;
+        }
+        x |= (uint64_t)(b & 0x7f) << sft;
+        sft += 7;
+    }
+    *out = 0;
+    return 0;
+}
+
+// decode.go:120-156 isMinLZ.  hdr = offset of the payload in the block.
+int parse_block_header(const uint8_t *src, size_t n, int *is_mlz, int *lits, size_t *hdr, int64_t *size) {
+    *is_mlz = 0;
+    *lits = 0;
+    *hdr = 0;
+    *size = 0;
+    if (n <= 1) {
+        if (n == 0) return MZCU_ERR_CORRUPT;
+        if (src[0] == 0) {
+            *is_mlz = 1;
+            *lits = 1;
+            *hdr = 1;
+            return MZCU_OK;
+        }
+    }
+    uint64_t v;
+    if (src[0] != 0) {
+        int k = get_uvarint(src, n, &v);
+        if (k <= 0 || v > 0xffffffffull) return MZCU_ERR_CORRUPT;
+        *size = (int64_t)v;
+        return MZCU_OK;
+    }
+    int k = get_uvarint(src + 1, n - 1, &v);
+    if (k <= 0 || v > 0xffffffffull) return MZCU_ERR_CORRUPT;
+    if (v > MZCU_MAX_BLOCK_SIZE) return MZCU_ERR_TOO_LARGE;
+    size_t rest = n - 1 - (size_t)k;
+    if (rest == 0) return MZCU_ERR_CORRUPT;
+    *hdr = 1 + (size_t)k;
+    if (v == 0) {
+        *is_mlz = 1;
+        *lits = 1;
+        *size = (int64_t)rest;
+        return MZCU_OK;
+    }
+    *size = (int64_t)v;
+    if (v < rest) return MZCU_ERR_CORRUPT;
+    *is_mlz = 1;
+    return MZCU_OK;
+}
+
+// encode.go:223-229 encodeUncompressed
+int64_t store_uncompressed(uint8_t *dst, size_t cap, const uint8_t *src, size_t n) {
+    if (n == 0) {
+        if (cap < 1) return fail(MZCU_ERR_DST_TOO_SMALL, "dst too small");
+        dst[0] = 0;
+        return 1;
+    }
+    if (cap < n + 2) return fail(MZCU_ERR_DST_TOO_SMALL, "dst too small");
+    dst[0] = 0;
+    dst[1] = 0;
+    memcpy(dst + 2, src, n);
+    return (int64_t)n + 2;
+}
+
+// Runs the seam-level encode for host buffers.  Blocks are packed densely on
+// the device (16-byte aligned starts); results land in the caller's layout.
+int host_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                       const uint64_t *dst_off, uint32_t *out_len) {
+    if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !out_len))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+        return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
+    if (nblk == 0) return MZCU_OK;
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    WsGuard g;
+    rc = ws_acquire(device, &g.w);
+    if (rc) return rc;
+    Workspace *w = g.w;
+
+    size_t src_bytes = 0, dst_bytes = 0;
+    for (int i = 0; i < nblk; i++) {
+        if (src_off[i + 1] < src_off[i] || dst_off[i + 1] < dst_off[i]) return fail(MZCU_ERR_INVALID_ARG, "offsets not monotonic");
+        size_t n = src_off[i + 1] - src_off[i];
+        if (n > MZCU_MAX_BLOCK_SIZE) return fail(MZCU_ERR_TOO_LARGE, "block %d larger than 8 MiB", i);
+        if (n >= 16 && dst_off[i + 1] - dst_off[i] < n + 2) return fail(MZCU_ERR_DST_TOO_SMALL, "block %d: dst capacity < MaxEncodedLen", i);
+        dst_bytes += (n + 2 + 15) & ~size_t(15);
+    }
+    src_bytes = src_off[nblk] - src_off[0];
+    rc = ws_reserve(w, src_bytes, dst_bytes, (size_t)nblk);
+    if (rc) return rc;
+    const size_t T = w->cap_tab;
+    uint64_t *h_sbeg = w->h_tab, *h_send = w->h_tab + T, *h_dbeg = w->h_tab + 2 * T;
+    uint64_t *d_sbeg = w->d_tab, *d_send = w->d_tab + T, *d_dbeg = w->d_tab + 2 * T;
+    uint32_t *d_out = reinterpret_cast<uint32_t *>(w->d_tab + 4 * T);
+    uint32_t *h_out = reinterpret_cast<uint32_t *>(w->h_tab + 4 * T);
+    // The device copy mirrors the caller's layout (kernels are alignment
+    // agnostic), so the whole batch moves with one H2D.
+    size_t dof = 0;
+    {
+        const size_t base = src_off[0];
+        const size_t total = src_off[nblk] - base;
+        for (int i = 0; i < nblk; i++) {
+            h_sbeg[i] = src_off[i] - base;
+            h_send[i] = src_off[i + 1] - base;
+        }
+        if (total) CU_TRY(cudaMemcpyAsync(w->d_src, src + base, total, cudaMemcpyHostToDevice, w->stream));
+    }
+    for (int i = 0; i < nblk; i++) {
+        size_t n = src_off[i + 1] - src_off[i];
+        h_dbeg[i] = dof;
+        dof += (n + 2 + 15) & ~size_t(15);
+    }
+    CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 3 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+    CU_TRY(cudaEventRecord(w->ev0, w->stream));
+    rc = launch_encode(device, level, nblk, w->d_src, d_sbeg, d_send, w->d_dst, d_dbeg, d_out, w->stream);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(w->ev1, w->stream));
+    CU_TRY(cudaMemcpyAsync(h_out, d_out, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    for (int i = 0; i < nblk; i++) {
+        out_len[i] = h_out[i];
+        if (h_out[i])
+            CU_TRY(cudaMemcpyAsync(dst + dst_off[i], w->d_dst + h_dbeg[i], h_out[i], cudaMemcpyDeviceToHost, w->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
+    return MZCU_OK;
+}
+
+// Seam-level decode for host buffers.  `sbeg/send` index into `src`.
+int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint8_t *dst,
+                       const uint64_t *dbeg, const uint64_t *dend, int32_t *status) {
+    if (nblk == 0) return MZCU_OK;
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    WsGuard g;
+    rc = ws_acquire(device, &g.w);
+    if (rc) return rc;
+    Workspace *w = g.w;
+    size_t dst_bytes = 0;
+    uint64_t lo = ~0ull, hi = 0;
+    bool dense = true;
+    for (int i = 0; i < nblk; i++) {
+        if (send[i] < sbeg[i] || dend[i] < dbeg[i]) return fail(MZCU_ERR_INVALID_ARG, "offsets not monotonic");
+        if (dend[i] - dbeg[i] > MZCU_MAX_BLOCK_SIZE) return fail(MZCU_ERR_TOO_LARGE, "block %d larger than 8 MiB", i);
+        if (send[i] > sbeg[i]) {
+            if (sbeg[i] < lo) lo = sbeg[i];
+            if (send[i] > hi) hi = send[i];
+        }
+        if (i + 1 < nblk && dend[i] != dbeg[i + 1]) dense = false;
+        dst_bytes += (dend[i] - dbeg[i] + 15) & ~size_t(15);
+    }
+    if (hi < lo) lo = hi = 0;
+    rc = ws_reserve(w, hi - lo, dst_bytes, (size_t)nblk);
+    if (rc) return rc;
+    const size_t T = w->cap_tab;
+    uint64_t *h = w->h_tab;
+    size_t dof = 0;
+    for (int i = 0; i < nblk; i++) {
+        size_t m = dend[i] - dbeg[i];
+        h[i] = send[i] > sbeg[i] ? sbeg[i] - lo : 0;
+        h[T + i] = send[i] > sbeg[i] ? send[i] - lo : 0;
+        h[2 * T + i] = dense ? dbeg[i] - dbeg[0] : dof;
+        h[3 * T + i] = h[2 * T + i] + m;
+        dof += (m + 15) & ~size_t(15);
+    }
+    if (hi > lo) CU_TRY(cudaMemcpyAsync(w->d_src, src + lo, hi - lo, cudaMemcpyHostToDevice, w->stream));
+    CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 4 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+    int32_t *d_status = reinterpret_cast<int32_t *>(w->d_tab + 4 * T);
+    int32_t *h_status = reinterpret_cast<int32_t *>(w->h_tab + 4 * T);
+    CU_TRY(cudaEventRecord(w->ev0, w->stream));
+    rc = launch_decode(device, nblk, w->d_src, w->d_tab, w->d_tab + T, w->d_dst, w->d_tab + 2 * T, w->d_tab + 3 * T, d_status,
+                       w->stream);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(w->ev1, w->stream));
+    CU_TRY(cudaMemcpyAsync(h_status, d_status, (size_t)nblk * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream));
+    if (dense) {
+        size_t total = dend[nblk - 1] - dbeg[0];
+        if (total) CU_TRY(cudaMemcpyAsync(dst + dbeg[0], w->d_dst, total, cudaMemcpyDeviceToHost, w->stream));
+    } else {
+        for (int i = 0; i < nblk; i++) {
+            size_t m = dend[i] - dbeg[i];
+            if (m) CU_TRY(cudaMemcpyAsync(dst + dbeg[i], w->d_dst + h[2 * T + i], m, cudaMemcpyDeviceToHost, w->stream));
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    for (int i = 0; i < nblk; i++) status[i] = h_status[i];
+    cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
+    return MZCU_OK;
+}
+
+}  // namespace
+
+// ============================ exported C ABI ================================
+extern "C" {
+
+int mzcu_abi_version(void) { return MZCU_ABI_VERSION; }
+const char *mzcu_last_error(void) { return g_err; }
+float mzcu_last_kernel_ms(void) { return g_last_kernel_ms; }
+
+int mzcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t mzcu_max_encoded_len(int64_t src_len) {
+    if (src_len < 0 || src_len > MZCU_MAX_BLOCK_SIZE) return -1;
+    if (src_len == 0) return 1;
+    return src_len + 2;
+}
+
+int mzcu_is_minlz(const uint8_t *block, size_t n, int *is_minlz, int64_t *size) {
+    int mlz, lits;
+    size_t hdr;
+    int64_t sz;
+    int rc = parse_block_header(block, n, &mlz, &lits, &hdr, &sz);
+    if (is_minlz) *is_minlz = mlz;
+    if (size) *size = sz;
+    if (rc) return fail(rc, "invalid block header");
+    return MZCU_OK;
+}
+
+int64_t mzcu_decoded_len(const uint8_t *block, size_t n) {
+    int mlz;
+    int64_t sz;
+    int rc = mzcu_is_minlz(block, n, &mlz, &sz);
+    return rc ? rc : sz;
+}
+
+int mzcu_encode_blocks_dev(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                           const uint64_t *dst_off, uint32_t *out_len, void *stream) {
+    if (nblk < 0 || (nblk > 0 && (!src || !src_off || !dst || !dst_off || !out_len)))
+        return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+        return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    return launch_encode(device, level, nblk, src, src_off, src_off + 1, dst, dst_off, out_len, (cudaStream_t)stream);
+}
+
+int mzcu_decode_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                           const uint64_t *dst_off, int32_t *status, void *stream) {
+    if (nblk < 0 || (nblk > 0 && (!src || !src_off || !dst || !dst_off || !status)))
+        return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    return launch_decode(device, nblk, src, src_off, src_off + 1, dst, dst_off, dst_off + 1, status, (cudaStream_t)stream);
+}
+
+int mzcu_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                       const uint64_t *dst_off, uint32_t *out_len) {
+    return host_encode_blocks(device, level, nblk, src, src_off, dst, dst_off, out_len);
+}
+
+int mzcu_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                       const uint64_t *dst_off, int32_t *status) {
+    if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !status))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    return host_decode_ranges(device, nblk, src, src_off, src_off + 1, dst, dst_off, dst_off + 1, status);
+}
+
+int mzcu_encode_batch(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                      const uint64_t *dst_off, uint64_t *enc_len) {
+    if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !enc_len))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    if (level != MZCU_LEVEL_UNCOMPRESSED && level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+        return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
+    // Per block: dst = 0x00 uvarint(n) tokens  (encode.go:87-90), with the
+    // token stream produced right behind the header.
+    std::vector<uint64_t> tsrc(nblk + 1), tdst((size_t)nblk + 1);
+    std::vector<uint32_t> out(nblk ? nblk : 1);
+    std::vector<int> hdr(nblk ? nblk : 1);
+    for (int i = 0; i < nblk; i++) {
+        size_t n = src_off[i + 1] - src_off[i];
+        size_t cap = dst_off[i + 1] - dst_off[i];
+        int64_t need = mzcu_max_encoded_len((int64_t)n);
+        if (need < 0) return fail(MZCU_ERR_TOO_LARGE, "block %d larger than 8 MiB", i);
+        if ((int64_t)cap < need) return fail(MZCU_ERR_DST_TOO_SMALL, "block %d: dst capacity < MaxEncodedLen", i);
+    }
+    bool any = false;
+    if (level != MZCU_LEVEL_UNCOMPRESSED)
+        for (int i = 0; i < nblk; i++) any |= (src_off[i + 1] - src_off[i]) >= 16;
+    std::vector<uint8_t> tmp;
+    std::vector<uint64_t> toff((size_t)nblk + 1, 0);
+    if (any) {
+        // token streams go to a scratch area with full MaxEncodedLen capacity
+        // (the header eats up to 5 bytes of the caller's n+2).
+        for (int i = 0; i < nblk; i++) toff[i + 1] = toff[i] + (src_off[i + 1] - src_off[i]) + 2;
+        tmp.resize(toff[nblk] + 16);
+        int rc = host_encode_blocks(device, level, nblk, src, src_off, tmp.data(), toff.data(), out.data());
+        if (rc) return rc;
+    }
+    for (int i = 0; i < nblk; i++) {
+        const uint8_t *s = src + src_off[i];
+        size_t n = src_off[i + 1] - src_off[i];
+        uint8_t *d = dst + dst_off[i];
+        size_t cap = dst_off[i + 1] - dst_off[i];
+        if (any && n >= 16 && out[i] > 0) {
+            d[0] = 0;
+            int h = 1 + put_uvarint(d + 1, n);
+            memcpy(d + h, tmp.data() + toff[i], out[i]);
+            enc_len[i] = (uint64_t)h + out[i];
+        } else {
+            int64_t m = store_uncompressed(d, cap, s, n);
+            if (m < 0) return (int)m;
+            enc_len[i] = (uint64_t)m;
+        }
+    }
+    return MZCU_OK;
+}
+
+int mzcu_decode_batch(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                      const uint64_t *dst_off, int64_t *dec_len) {
+    if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !dec_len))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    std::vector<uint64_t> sbeg(nblk ? nblk : 1), send(nblk ? nblk : 1), dbeg(nblk ? nblk : 1), dend(nblk ? nblk : 1);
+    std::vector<int32_t> status(nblk ? nblk : 1, 0);
+    bool any = false;
+    for (int i = 0; i < nblk; i++) {
+        const uint8_t *b = src + src_off[i];
+        size_t n = src_off[i + 1] - src_off[i];
+        size_t cap = dst_off[i + 1] - dst_off[i];
+        int mlz, lits;
+        size_t hdr;
+        int64_t sz;
+        int rc = parse_block_header(b, n, &mlz, &lits, &hdr, &sz);
+        sbeg[i] = send[i] = src_off[i];
+        dbeg[i] = dend[i] = dst_off[i];
+        if (rc) {
+            dec_len[i] = rc;
+        } else if (!mlz) {
+            dec_len[i] = MZCU_ERR_UNSUPPORTED;
+        } else if ((size_t)sz > cap) {
+            dec_len[i] = MZCU_ERR_DST_TOO_SMALL;
+        } else if (lits) {
+            memcpy(dst + dst_off[i], b + hdr, (size_t)sz);  // decode.go:55-57
+            dec_len[i] = sz;
+        } else {
+            sbeg[i] = src_off[i] + hdr;
+            send[i] = src_off[i + 1];
+            dend[i] = dst_off[i] + (uint64_t)sz;
+            dec_len[i] = sz;
+            any = true;
+        }
+    }
+    if (any) {
+        int rc = host_decode_ranges(device, nblk, src, sbeg.data(), send.data(), dst, dbeg.data(), dend.data(), status.data());
+        if (rc) return rc;
+        for (int i = 0; i < nblk; i++)
+            if (status[i] != 0) dec_len[i] = MZCU_ERR_CORRUPT;
+    }
+    return MZCU_OK;
+}
+
+int64_t mzcu_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, int level) {
+    int64_t need = mzcu_max_encoded_len((int64_t)n);
+    if (need < 0) return fail(MZCU_ERR_TOO_LARGE, "block larger than 8 MiB");
+    if (n < 16) return store_uncompressed(dst, dst_cap, src, n);  // encode.go:83-85
+    if ((int64_t)dst_cap < need) return fail(MZCU_ERR_DST_TOO_SMALL, "dst capacity < MaxEncodedLen");
+    uint64_t so[2] = {0, n}, dof[2] = {0, dst_cap}, el = 0;
+    int rc = mzcu_encode_batch(-1, level, 1, src, so, dst, dof, &el);
+    return rc ? rc : (int64_t)el;
+}
+
+int64_t mzcu_try_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, int level) {
+    // encode.go:168-207: nil unless compressible and d+n < len(src)
+    int64_t need = mzcu_max_encoded_len((int64_t)n);
+    if (need < 0 || (int64_t)dst_cap < need || n < 16) return 0;
+    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED) return 0;
+    std::vector<uint8_t> tmp(n + 18);
+    uint64_t so[2] = {0, n}, dof[2] = {0, n + 2};
+    uint32_t out = 0;
+    int rc = host_encode_blocks(-1, level, 1, src, so, tmp.data(), dof, &out);
+    if (rc) return rc;
+    dst[0] = 0;
+    int h = 1 + put_uvarint(dst + 1, n);
+    if (out > 0 && (size_t)h + out < n) {
+        memcpy(dst + h, tmp.data(), out);
+        return (int64_t)h + out;
+    }
+    return 0;
+}
+
+int64_t mzcu_decode(uint8_t *dst, size_t dst_cap, const uint8_t *block, size_t n) {
+    uint64_t so[2] = {0, n}, dof[2] = {0, dst_cap};
+    int64_t dl = 0;
+    int rc = mzcu_decode_batch(-1, 1, block, so, dst, dof, &dl);
+    if (rc) return rc;
+    if (dl < 0) return fail((int)dl, "decode failed (%lld)", (long long)dl);
+    return dl;
+}
+
+void *mzcu_host_alloc(size_t n) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, n ? n : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void mzcu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+"""GPU parity tests: every call goes through the C ABI of libminlz_cuda.so and
+is checked bit-for-bit against the CPU oracle (tests-only) on the same inputs.
+
+Reference tests mirrored: minlz_test.go:632 TestDecodeGoldenInput, :138-194
+roundtrip (+ :202-253 drivers, :780, :1538), decode_asm_test.go:28-352,
+fuzz_test.go:31 FuzzEncodingBlocks, :120 FuzzDecodeBlock.
+"""
+import numpy as np
+import pytest
+
+import corpus
+import patterns
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import minlz_b200 as mz  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+    assert mz.device_count() >= 1
+
+
+def _cat(blobs):
+    sizes = [len(b) for b in blobs]
+    off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+    np.cumsum(sizes, out=off[1:])
+    flat = np.frombuffer(b"".join(blobs), dtype=np.uint8) if off[-1] else np.zeros(0, dtype=np.uint8)
+    return flat, off
+
+
+def _all_inputs():
+    items = patterns.reference_patterns() + patterns.roundtrip_inputs()
+    items += [("twain", open(corpus.golden_path("Mark.Twain-Tom.Sawyer.txt"), "rb").read())]
+    for z in ("enc_regressions.zip", "block-corpus-raw-sample.zip", "block-corpus-enc-sample.zip"):
+        items += list(corpus.load_zip(corpus.golden_path(z)))
+    return items
+
+
+# ---------------------------------------------------------------- decode ----
+
+def test_decode_golden():
+    want = open(corpus.golden_path("Mark.Twain-Tom.Sawyer.txt"), "rb").read()
+    mzb = open(corpus.golden_path("Mark.Twain-Tom.Sawyer.txt.mzb"), "rb").read()
+    assert mz.DecodedLen(mzb) == len(want)
+    assert mz.Decode(None, mzb) == want
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_decode_oracle_encoded_inputs(oracle, level):
+    """Blocks produced by the oracle encoders decode to the original on the GPU
+    (seam level: token streams without header, exact dst length)."""
+    items = [(n, d) for n, d in _all_inputs() if len(d) >= 1]
+    streams, raws = [], []
+    for name, data in items:
+        tok = oracle.encode_block(data, level)
+        if not tok:
+            continue  # incompressible or < 16 bytes: no token stream at the seam
+        streams.append(tok)
+        raws.append(data)
+    assert len(streams) > 100
+    src, soff = _cat(streams)
+    _, doff = _cat(raws)
+    dst, status = mz.decode_blocks(src, soff, doff)
+    assert not status.any(), np.nonzero(status)[0][:10]
+    want = b"".join(raws)
+    got = dst.tobytes()
+    if got != want:
+        for i in range(len(raws)):
+            a, b = int(doff[i]), int(doff[i + 1])
+            assert got[a:b] == want[a:b], "block %d (%d bytes) differs" % (i, b - a)
+
+
+def test_decode_adversarial_blocks_match_oracle(oracle):
+    """fuzz_test.go:120: corrupt / hostile blocks.  Accept/reject and bytes must
+    equal the oracle's; dst must not be written outside its range."""
+    blobs = [b for _, b in corpus.load_zip(corpus.golden_path("block-corpus-dec.zip"))]
+    blobs += [b for _, b in corpus.load_zip(corpus.golden_path("dec-block-regressions.zip"))]
+    res = mz.DecodeBatch(blobs)
+    n_ok = 0
+    for blob, r in zip(blobs, res):
+        want = oracle.decode(blob)
+        if isinstance(want, bytes):
+            assert r == want
+            n_ok += 1
+        elif want == oracle.ERR_UNSUPPORTED:
+            assert isinstance(r, mz.ErrUnsupported)
+        elif want == oracle.ERR_TOO_LARGE:
+            assert isinstance(r, mz.ErrTooLarge)
+        else:
+            assert isinstance(r, mz.ErrCorrupt), (want, r)
+    assert n_ok >= 3
+
+
+def _mutations(oracle, rng, data, level, count):
+    tok = bytearray(oracle.encode_block(data, level))
+    out = []
+    for _ in range(count):
+        t = bytearray(tok)
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                t[int(rng.integers(0, len(t)))] = int(rng.integers(0, 256))
+        elif kind == 1:
+            t = t[:int(rng.integers(0, len(t)))]
+        elif kind == 2:
+            p = int(rng.integers(0, len(t)))
+            t[p:p] = bytes(rng.integers(0, 256, int(rng.integers(1, 8)), dtype=np.uint8))
+        else:
+            p = int(rng.integers(0, len(t)))
+            del t[p:p + int(rng.integers(1, 8))]
+        out.append(bytes(t))
+    return out
+
+
+def test_decode_mutated_streams_match_oracle(oracle):
+    """Seam-level fuzz: mutated token streams against the oracle's status and
+    bytes, with guard bytes around every dst range."""
+    rng = np.random.default_rng(7)
+    base = [patterns.generate_test_data(5000), patterns.fused_lits(10000), patterns.offset2(6000),
+            open(corpus.golden_path("Mark.Twain-Tom.Sawyer.txt"), "rb").read()]
+    streams, dlens = [], []
+    for data in base:
+        for level in (1, 2):
+            for m in _mutations(oracle, rng, data, level, 150):
+                streams.append(m)
+                dlens.append(len(data) if rng.random() < 0.8 else int(rng.integers(0, 2 * len(data))))
+    src, soff = _cat(streams)
+    doff = np.zeros(len(dlens) + 1, dtype=np.uint64)
+    np.cumsum(dlens, out=doff[1:])
+    dst, status = mz.decode_blocks(src, soff, doff)
+    n_ok = n_bad = 0
+    for i, (st, dl) in enumerate(zip(streams, dlens)):
+        wst, wout = oracle.decode_block(st, dl)
+        assert int(status[i]) == wst, "stream %d: status %d, oracle %d" % (i, status[i], wst)
+        if wst == 0:
+            assert dst[int(doff[i]):int(doff[i + 1])].tobytes() == wout
+            n_ok += 1
+        else:
+            n_bad += 1
+    assert n_ok > 10 and n_bad > 100
+
+
+def test_decode_device_api_no_overrun(oracle):
+    """Device-pointer entry point.  Guard ranges (empty stream, 64 bytes of
+    dst: corrupt, nothing may be written) sit between the real blocks and must
+    keep their 0xfe fill (fuzz_test.go:169-182 uses guard bytes the same way)."""
+    data = [patterns.generate_test_data(100000), patterns.short_repeat(3, 9), b"x" * 70000, patterns.offset2(65549)]
+    streams = [oracle.encode_block(d, 1) for d in data]
+    streams.append(streams[0][:-3])  # truncated -> corrupt, may only touch its own range
+    lens = [len(d) for d in data] + [len(data[0])]
+    g_streams, g_lens = [], []
+    for s_, n in zip(streams, lens):
+        g_streams += [s_, b""]
+        g_lens += [n, 64]
+    src, soff = _cat(g_streams)
+    d_off = np.zeros(len(g_lens) + 1, dtype=np.int64)
+    np.cumsum(g_lens, out=d_off[1:])
+    dev = torch.device("cuda:0")
+    t_src = torch.from_numpy(src.copy()).to(dev)
+    t_soff = torch.from_numpy(soff.astype(np.int64)).to(dev)
+    t_doff = torch.from_numpy(d_off).to(dev)
+    t_dst = torch.full((int(d_off[-1]),), 0xfe, dtype=torch.uint8, device=dev)
+    t_status = torch.full((len(g_lens),), -1, dtype=torch.int32, device=dev)
+    mz.decode_blocks_dev(t_src, t_soff, t_dst, t_doff, t_status)
+    torch.cuda.synchronize()
+    status = t_status.cpu().numpy()
+    out = t_dst.cpu().numpy()
+    for k in range(len(g_lens) // 2):
+        g0, g1 = d_off[2 * k + 1], d_off[2 * k + 2]
+        assert status[2 * k + 1] == 1                      # guard: d != len(dst)
+        assert (out[g0:g1] == 0xfe).all(), "guard %d overwritten" % k
+    for k, d in enumerate(data):
+        assert status[2 * k] == 0
+        assert out[d_off[2 * k]:d_off[2 * k + 1]].tobytes() == d
+    assert status[2 * len(data)] == 1
+
+
+# ---------------------------------------------------------------- encode ----
+
+@pytest.mark.parametrize("level", [1])
+def test_encode_bytes_equal_oracle(oracle, level):
+    """Seam level: the CUDA encoder's token stream is byte-identical to the
+    oracle's restatement of the Go path, including the 0 = incompressible."""
+    items = _all_inputs()
+    raws = [d for _, d in items]
+    src, soff = _cat(raws)
+    dst, doff, out_len = mz.encode_blocks(src, soff, level)
+    bad = []
+    for i, (name, data) in enumerate(items):
+        want = oracle.encode_block(data, level)
+        got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
+        if got != want:
+            bad.append((name, len(data), len(got), len(want)))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("level", [1])
+def test_encode_api_roundtrip(oracle, level):
+    """minlz_test.go:138-194 roundtrip through the block API mirror."""
+    for name, data in patterns.roundtrip_inputs()[:24] + patterns.reference_patterns()[:12]:
+        enc = mz.Encode(None, data, level)
+        assert len(enc) <= mz.MaxEncodedLen(len(data))
+        assert enc == oracle.encode(data, level), name
+        assert mz.DecodedLen(enc) == len(data)
+        assert mz.Decode(None, enc) == data, name
+        te = mz.TryEncode(None, data, level)
+        assert te == oracle.try_encode(data, level)
+
+
+def test_api_edge_cases(oracle):
+    # encode.go:83-85,223-229 and decode.go:55-57
+    assert mz.Encode(None, b"", 1) == b"\x00"
+    for n in range(1, 16):
+        d = bytes(range(n))
+        assert mz.Encode(None, d, 1) == b"\x00\x00" + d
+        assert mz.Decode(None, b"\x00\x00" + d) == d
+    assert mz.Decode(None, b"\x00") == b""
+    with pytest.raises(mz.ErrInvalidLevel):
+        mz.Encode(None, b"x" * 100, 9)
+    with pytest.raises(mz.ErrTooLarge):
+        mz.Encode(None, bytes((8 << 20) + 1), 1)
+    rnd = np.random.default_rng(3).integers(0, 256, 100000, dtype=np.uint8).tobytes()
+    assert mz.Encode(None, rnd, 1) == b"\x00\x00" + rnd       # incompressible -> stored
+    assert mz.TryEncode(None, rnd, 1) is None
+    assert mz.Encode(None, rnd, mz.LevelUncompressed) == b"\x00\x00" + rnd
+    with pytest.raises(mz.ErrCorrupt) as ei:
+        good = oracle.encode(b"abcdefgh" * 100, 1)
+        mz.Decode(None, good[:-2])
+    assert ei.value.partial is not None and len(ei.value.partial) == 800
+    with pytest.raises(mz.ErrUnsupported):
+        mz.Decode(None, b"\x05hello")  # Snappy/S2 fallback lives in host Go
+    big = bytes(8 << 20)
+    enc = mz.Encode(None, big, 1)
+    assert enc == oracle.encode(big, 1) and mz.Decode(None, enc) == big
+
+
+def test_synthetic_batch_parity(oracle):
+    """BASELINE configs 2/3 shape at a size the oracle finishes in seconds:
+    32 x 1 MiB json blocks, encode bytes == oracle, decode == input."""
+    import synth
+    blocks = synth.make_blocks("json", 32, 1 << 20, device="cuda").cpu().numpy()
+    src = blocks.reshape(-1)
+    soff = (np.arange(33, dtype=np.uint64) << 20)
+    dst, doff, out_len = mz.encode_blocks(src, soff, 1)
+    streams = []
+    for i in range(32):
+        want = oracle.encode_block(blocks[i], 1)
+        got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
+        assert got == want, "block %d" % i
+        streams.append(got)
+    for level in (1, 2):
+        enc = [oracle.encode_block(blocks[i], level) for i in range(32)]
+        csrc, csoff = _cat(enc)
+        out, status = mz.decode_blocks(csrc, csoff, soff)
+        assert not status.any()
+        assert np.array_equal(out, src)
+
+
+def test_full_size_roundtrip_property():
+    """BASELINE configs 2+3 at full size (4096 x 1 MiB): encode on the GPU,
+    decode on the GPU, output equals input; all device resident."""
+    import synth
+    dev = torch.device("cuda:0")
+    nblk, bs = 4096, 1 << 20
+    src = synth.make_blocks("json", nblk, bs, device=dev).reshape(-1)
+    soff = torch.arange(nblk + 1, dtype=torch.int64, device=dev) * bs
+    cap = bs + 16
+    doff = torch.arange(nblk + 1, dtype=torch.int64, device=dev) * cap
+    enc = torch.empty(nblk * cap, dtype=torch.uint8, device=dev)
+    out_len = torch.zeros(nblk, dtype=torch.int32, device=dev)
+    mz.encode_blocks_dev(src, soff, enc, doff, out_len, 1)
+    torch.cuda.synchronize()
+    lens = out_len.to(torch.int64)
+    assert int(lens.min()) > 0 and int(lens.max()) < bs // 2
+    # compact the token streams so that src_off is a dense offset table
+    coff = torch.zeros(nblk + 1, dtype=torch.int64, device=dev)
+    coff[1:] = torch.cumsum(lens, 0)
+    idx = torch.arange(int(coff[-1]), device=dev)
+    blk = torch.searchsorted(coff[1:], idx, right=True)
+    comp = enc[doff[blk] + (idx - coff[blk])]
+    del enc, idx, blk
+    dec = torch.empty(nblk * bs, dtype=torch.uint8, device=dev)
+    status = torch.full((nblk,), -1, dtype=torch.int32, device=dev)
+    mz.decode_blocks_dev(comp, coff, dec, soff, status)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    assert torch.equal(dec, src)
