@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- MinLZ block encode+decode throughput on B200 (one JSON line).
+
+Workload (BASELINE.json configs[1]+[2], the configuration the metric is quoted
+on): 4096 x 1 MiB synthetic JSON-like blocks per GPU.  One step = LevelFastest
+encode of the whole batch (encode_l1 kernel + dense pack), then decode of the
+packed token streams (decode kernel), all through the C ABI of
+libminlz_cuda.so.  `value` = uncompressed bytes / (encode + decode time), data
+resident in HBM; `e2e` = the same round trip through the host-pointer C ABI
+calls with pinned host buffers (H2D and D2H inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                  [--blocks B] [--block-size S] [--kind json]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "uncompressed GB/s encode+decode, 1 MB blocks, 1/2/4/8 GPU vs host asm"
+UNIT = "GB/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu summary, or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+            f = [x.strip() for x in out.strip().split(",")]
+            self.samples.append(float(f[0]))
+            self.max_mhz = float(f[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._once()
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_round_trip(host_blocks, nthreads, repeats=2):
+    """Times the oracle port (test/bench infrastructure) on host cores:
+    L1 encode + decode of `host_blocks` ([n, bs] uint8 numpy).  Returns GB/s
+    of uncompressed bytes over the encode+decode time, and the parts."""
+    import numpy as np
+    from oracle import binding as oracle
+    oracle.build()
+    n, bs = host_blocks.shape
+    src = host_blocks.reshape(-1)
+    soff = np.arange(n + 1, dtype=np.uint64) * bs
+    cap = bs + 16
+    doff = np.arange(n + 1, dtype=np.uint64) * cap
+    enc = np.zeros(n * cap, dtype=np.uint8)  # pre-touched: no page faults in the timed region
+    best_e = best_d = 1e30
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out_len = oracle.encode_batch_mt(1, src, soff, enc, doff, nthreads)
+        t1 = time.perf_counter()
+        best_e = min(best_e, t1 - t0)
+    assert (out_len > 0).all()
+    coff = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(out_len, out=coff[1:])
+    comp = np.empty(int(coff[-1]), dtype=np.uint8)
+    for i in range(n):
+        comp[int(coff[i]):int(coff[i + 1])] = enc[int(doff[i]):int(doff[i]) + int(out_len[i])]
+    dec = np.zeros(n * bs, dtype=np.uint8)
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        status = oracle.decode_batch_mt(comp, coff, dec, soff, nthreads)
+        t1 = time.perf_counter()
+        best_d = min(best_d, t1 - t0)
+    assert not status.any() and np.array_equal(dec, src)
+    total = n * bs
+    return {"value": total / (best_e + best_d) / 1e9, "encode_gbps": total / best_e / 1e9,
+            "decode_gbps": total / best_d / 1e9, "seconds": best_e + best_d}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the
+    box's host cores.  The Go/asm reference cannot be built here (no Go
+    toolchain), so this is the oracle port of its pure-Go path, all cores."""
+    import numpy as np
+    import torch
+    import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nsample = min(args.blocks, args.cpu_blocks)
+    blocks = synth.make_blocks(args.kind, nsample, args.block_size, device="cpu").numpy()
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_round_trip(blocks[: max(1, nsample // 8)], cores, repeats=1)
+    t_tot = 0.0
+    res = None
+    for _ in range(args.steps):
+        res = cpu_round_trip(blocks, cores, repeats=1)
+        t_tot += res["seconds"]
+    value = nsample * args.block_size * args.steps / t_tot / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_tot / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d x %d B %s blocks per step, L1 encode + decode, oracle port of the Go path "
+                                   "(Go/asm reference not buildable: no Go toolchain)" % (nsample, args.block_size, args.kind),
+                         "encode_gbps": round(res["encode_gbps"], 4), "decode_gbps": round(res["decode_gbps"], 4)},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "configs[1]+[2]: %d x %d B synthetic %s blocks per GPU, LevelFastest encode (encode_l1) then "
+                        "batched decode of the packed token streams" % (args.blocks, args.block_size, args.kind),
+            "blocks_per_gpu": args.blocks, "block_size": args.block_size, "level": 1,
+            "cache": "inputs (%.1f GB per pass) larger than the 126 MB L2, no flush needed" %
+                     (args.blocks * args.block_size / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--blocks", type=int, default=4096)
+    ap.add_argument("--block-size", type=int, default=1 << 20)
+    ap.add_argument("--kind", default="json")
+    ap.add_argument("--cpu-blocks", type=int, default=1024, help="bounded sample for the CPU legs")
+    ap.add_argument("--e2e-blocks", type=int, default=1024, help="blocks per e2e step (host buffers)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import minlz_b200 as mz
+    import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nblk, bs = args.blocks, args.block_size
+
+    # ---- synthetic input, resident in HBM; independent blocks shard by rank
+    src = synth.make_blocks(args.kind, nblk, bs, device=dev, first=rank * nblk).reshape(-1)
+    soff = torch.arange(nblk + 1, dtype=torch.int64, device=dev) * bs
+    cap = bs + 16
+    eoff = torch.arange(nblk + 1, dtype=torch.int64, device=dev) * cap
+    enc = torch.empty(nblk * cap, dtype=torch.uint8, device=dev)
+    out_len = torch.zeros(nblk, dtype=torch.int32, device=dev)
+    comp = torch.empty(nblk * bs, dtype=torch.uint8, device=dev)
+    coff = torch.zeros(nblk + 1, dtype=torch.int64, device=dev)
+    dec = torch.empty(nblk * bs, dtype=torch.uint8, device=dev)
+    status = torch.zeros(nblk, dtype=torch.int32, device=dev)
+    all_len = torch.zeros(world * nblk, dtype=torch.int32, device=dev) if world > 1 else None
+
+    stream = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step(timed):
+        if timed is not None:
+            ev[0].record(stream)
+        mz.encode_blocks_dev(src, soff, enc, eoff, out_len, mz.LevelFastest)
+        if timed is not None:
+            ev[1].record(stream)
+        mz.pack_blocks_dev(enc, eoff, out_len, comp, coff)
+        if world > 1:
+            # the one real exchange of the sharded stream: every rank learns all
+            # compressed block sizes (stream order = rank order), 4 B per block
+            dist.all_gather_into_tensor(all_len, out_len)
+        if timed is not None:
+            ev[2].record(stream)
+        mz.decode_blocks_dev(comp, coff, dec, soff, status)
+        if timed is not None:
+            ev[3].record(stream)
+            torch.cuda.synchronize()
+            timed["enc"] += ev[0].elapsed_time(ev[1])
+            timed["pack"] += ev[1].elapsed_time(ev[2])
+            timed["dec"] += ev[2].elapsed_time(ev[3])
+
+    for _ in range(args.warmup):
+        step(None)
+    torch.cuda.synchronize()
+    # correctness gate before timing: the round trip must reproduce the input
+    if args.warmup == 0:
+        step(None)
+        torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0, "decode reported corrupt blocks"
+    assert int((out_len <= 0).sum()) == 0, "encoder returned incompressible on compressible data"
+    assert torch.equal(dec, src), "round trip mismatch"
+    comp_bytes = int(coff[-1])
+
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    parts = {"enc": 0.0, "pack": 0.0, "dec": 0.0}
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        t_start.record(stream)
+        for _ in range(args.steps):
+            step(parts)
+        t_end.record(stream)
+        torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    tms = torch.tensor([total_ms, parts["enc"], parts["pack"], parts["dec"]], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, pack_ms, dec_ms = [float(x) for x in tms.tolist()]
+    K = args.steps
+    U = nblk * bs
+    step_ms = total_ms / K
+    value = world * U / (step_ms * 1e-3) / 1e9
+
+    # ---- e2e: host-pointer C ABI calls with pinned buffers -----------------
+    e2e = None
+    if not args.no_e2e:
+        nb = min(nblk, args.e2e_blocks)
+        h_src = torch.empty(nb * bs, dtype=torch.uint8).pin_memory()
+        h_src.copy_(src[: nb * bs])
+        h_enc = torch.empty(nb * cap, dtype=torch.uint8).pin_memory()
+        h_dec = torch.empty(nb * bs, dtype=torch.uint8).pin_memory()
+        h_comp = torch.empty(nb * bs, dtype=torch.uint8).pin_memory()
+        n_src, n_enc, n_dec, n_comp = h_src.numpy(), h_enc.numpy(), h_dec.numpy(), h_comp.numpy()
+        hs = np.arange(nb + 1, dtype=np.uint64) * bs
+        he = np.arange(nb + 1, dtype=np.uint64) * cap
+        hlen = np.zeros(nb, dtype=np.uint32)
+        hst = np.zeros(nb, dtype=np.int32)
+
+        def e2e_step():
+            mz.encode_blocks_into(n_src, hs, n_enc, he, hlen, mz.LevelFastest, device=local)
+            hc = np.zeros(nb + 1, dtype=np.uint64)
+            np.cumsum(hlen, out=hc[1:])
+            # host-side hand-off of the compressed blocks (what a Writer does)
+            for i in range(nb):
+                n_comp[int(hc[i]):int(hc[i + 1])] = n_enc[int(he[i]):int(he[i]) + int(hlen[i])]
+            mz.decode_blocks_into(n_comp, hc, n_dec, hs, hst, device=local)
+            return int(hc[-1])
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        assert np.array_equal(n_dec, n_src) and not hst.any()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ek = max(1, min(K, 3))
+        for _ in range(ek):
+            cb = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ek
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        e2e = {"value": round(world * nb * bs / dt / 1e9, 4), "unit": UNIT,
+               "h2d_bytes_per_step": int(nb * bs + cb + 2 * 8 * (nb + 1) * 2),
+               "d2h_bytes_per_step": int(cb + nb * bs + 8 * nb),
+               "blocks_per_step": nb, "ms_per_step": round(dt * 1e3, 3),
+               "api": "mzcu_encode_blocks + mzcu_decode_blocks (host pointers, pinned)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    enc_bytes = U + comp_bytes          # algorithmic: read source once, write tokens once
+    dec_bytes = comp_bytes + U          # read tokens once, write output once
+    enc_gbs = enc_bytes / (enc_ms / K * 1e-3) / 1e9
+    dec_gbs = dec_bytes / (dec_ms / K * 1e-3) / 1e9
+    dominant_is_enc = enc_ms >= dec_ms
+    roof = {"bound": "hbm", "kernel": "encode_l1_kernel" if dominant_is_enc else "decode kernel",
+            "achieved": round(enc_gbs if dominant_is_enc else dec_gbs, 3), "peak": peak, "unit": "GB/s",
+            "frac": round((enc_gbs if dominant_is_enc else dec_gbs) / peak, 5),
+            "traffic": ncu_traffic("encode" if dominant_is_enc else "decode"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": enc_bytes if dominant_is_enc else dec_bytes,
+            "share_of_step": round((enc_ms if dominant_is_enc else dec_ms) / total_ms, 4)}
+    roof_dec = {"bound": "hbm", "kernel": "decode kernel", "achieved": round(dec_gbs, 3), "peak": peak, "unit": "GB/s",
+                "frac": round(dec_gbs / peak, 5), "traffic": ncu_traffic("decode"),
+                "algorithmic_bytes_per_launch": dec_bytes, "share_of_step": round(dec_ms / total_ms, 4)}
+    roof_enc = {"bound": "hbm", "kernel": "encode_l1_kernel", "achieved": round(enc_gbs, 3), "peak": peak, "unit": "GB/s",
+                "frac": round(enc_gbs / peak, 5), "traffic": ncu_traffic("encode"),
+                "algorithmic_bytes_per_launch": enc_bytes, "share_of_step": round(enc_ms / total_ms, 4)}
+
+    cpu = None
+    if not args.no_cpu and world >= 1:
+        cores = os.cpu_count() or 1
+        nsample = min(nblk, args.cpu_blocks)
+        hb = src[: nsample * bs].cpu().numpy().reshape(nsample, bs)
+        r = cpu_round_trip(hb, cores, repeats=2)
+        cpu = {"value": round(r["value"], 4), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d of the %d blocks, L1 encode + decode, best of 2, oracle port of the Go path "
+                         "(the Go/asm reference cannot be built here: no Go toolchain)" % (nsample, nblk),
+               "encode_gbps": round(r["encode_gbps"], 4), "decode_gbps": round(r["decode_gbps"], 4)}
+
+    line = {
+        "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+        "encode_gbps": round(world * U / (enc_ms / K * 1e-3) / 1e9, 3),
+        "decode_gbps": round(world * U / (dec_ms / K * 1e-3) / 1e9, 3),
+        "ms": {"encode": round(enc_ms / K, 4), "pack": round(pack_ms / K, 4), "decode": round(dec_ms / K, 4)},
+        "ratio": round(U / comp_bytes, 4),
+        "roofline": roof, "roofline_decode": roof_dec, "roofline_encode": roof_enc,
+        "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
+        "gpu_launches": K * 4,  # per step: encode_l1, scan_lengths, pack_blocks, decode
+        "parity": "round trip verified bit-exact before timing",
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,15 @@ int mzcu_encode_blocks_dev(int device, int level, int nblk, const uint8_t *src, 
 int mzcu_decode_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                            const uint64_t *dst_off, int32_t *status, void *stream);
 
+/* Packs encoder output into a dense stream: block i (len[i] bytes at
+ * src + src_off[i]) is copied to dst + dst_off[i], where dst_off (device
+ * uint64[nblk+1], written by this call) is the exclusive prefix sum of len.
+ * The batch analogue of the ordered result hand-off in writer.go:214-272; the
+ * result is directly consumable by mzcu_decode_blocks_dev.  dst must hold
+ * sum(len) bytes (<= sum of capacities). */
+int mzcu_pack_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, const uint32_t *len,
+                         uint8_t *dst, uint64_t *dst_off, void *stream);
+
 /* ---- seam level, host pointers (synchronous; H2D + kernel + D2H) -------
  * Same contracts with host memory; pinned memory (mzcu_host_alloc) makes the
  * copies asynchronous-capable and ~2x faster.  device < 0 = current device. */

@@ -295,5 +295,31 @@ def decode_blocks_dev(src, src_off, dst, dst_off, status, stream=None):
         _raise(r)
 
 
+def pack_blocks_dev(src, src_off, lens, dst, dst_off, stream=None):
+    """Dense-packs encoder output on the device; writes dst_off (int64, nblk+1)."""
+    nblk = lens.numel()
+    r = _lib.load().mzcu_pack_blocks_dev(src.device.index, nblk, src.data_ptr(), src_off.data_ptr(), lens.data_ptr(),
+                                         dst.data_ptr(), dst_off.data_ptr(), _stream_ptr(stream))
+    if r < 0:
+        _raise(r)
+
+
+def encode_blocks_into(src, src_off, dst, dst_off, out_len, level, device=-1):
+    """Host numpy buffers, caller-allocated (e.g. pinned): the C ABI host call."""
+    nblk = len(src_off) - 1
+    r = _lib.load().mzcu_encode_blocks(device, level, nblk, src.ctypes.data, src_off.ctypes.data, dst.ctypes.data,
+                                       dst_off.ctypes.data, out_len.ctypes.data)
+    if r < 0:
+        _raise(r)
+
+
+def decode_blocks_into(src, src_off, dst, dst_off, status, device=-1):
+    nblk = len(src_off) - 1
+    r = _lib.load().mzcu_decode_blocks(device, nblk, src.ctypes.data, src_off.ctypes.data, dst.ctypes.data,
+                                       dst_off.ctypes.data, status.ctypes.data)
+    if r < 0:
+        _raise(r)
+
+
 def last_kernel_ms():
     return float(_lib.load().mzcu_last_kernel_ms())

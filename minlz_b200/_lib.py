@@ -16,6 +16,7 @@ SYMBOLS = {
     "mzcu_is_minlz": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "mzcu_encode_blocks_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "mzcu_decode_blocks_dev": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "mzcu_pack_blocks_dev": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "mzcu_encode_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "mzcu_decode_blocks": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "mzcu_encode": (C.c_int64, [_P, C.c_size_t, _P, C.c_size_t, C.c_int]),

@@ -17,6 +17,7 @@
 
 #include "mz_decode.cuh"
 #include "mz_encode_l1.cuh"
+#include "mz_pack.cuh"
 
 namespace {
 
@@ -97,6 +98,18 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
     } else {
         return fail(MZCU_ERR_INVALID_LEVEL, "level %d not implemented on device", level);
     }
+    CU_TRY(cudaGetLastError());
+    return MZCU_OK;
+}
+
+int launch_pack(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint32_t *len, uint8_t *dst,
+                uint64_t *off, cudaStream_t stream) {
+    if (nblk == 0) return MZCU_OK;
+    mz::scan_lengths_kernel<<<1, 1024, 0, stream>>>(nblk, len, off);
+    CU_TRY(cudaGetLastError());
+    int grid = g_dev[device].num_sms * 8;
+    if (grid > nblk) grid = nblk;
+    mz::pack_blocks_kernel<<<grid, 256, 0, stream>>>(nblk, src, sbeg, len, dst, off);
     CU_TRY(cudaGetLastError());
     return MZCU_OK;
 }
@@ -457,6 +470,17 @@ int mzcu_decode_blocks_dev(int device, int nblk, const uint8_t *src, const uint6
     int rc = init_device(device);
     if (rc) return rc;
     return launch_decode(device, nblk, src, src_off, src_off + 1, dst, dst_off, dst_off + 1, status, (cudaStream_t)stream);
+}
+
+int mzcu_pack_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, const uint32_t *len,
+                         uint8_t *dst, uint64_t *dst_off, void *stream) {
+    if (nblk < 0 || (nblk > 0 && (!src || !src_off || !len || !dst || !dst_off)))
+        return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    return launch_pack(device, nblk, src, src_off, len, dst, dst_off, (cudaStream_t)stream);
 }
 
 int mzcu_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
