@@ -12,6 +12,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef MZO_STATS
+uint64_t mzo_stats[16];
+#define STAT(i) (mzo_stats[i]++)
+#else
+#define STAT(i) ((void)0)
+#endif
+
 /* ---- encode.go:30-58 constants ---------------------------------------- */
 enum {
     kMaxCopy1Offset = 1024,
@@ -279,6 +286,7 @@ static int64_t encode_l1(uint8_t *dst, const uint8_t *src, int n, int tableBits,
     for (;;) {
         candidate = 0;
         for (;;) {
+            STAT(0);
             int nextS = s + ((s - nextEmit) >> skipLog) + 4; /* :79 */
             if (nextS > sLimit) goto emit_remainder;          /* :80-82 */
             int minSrcPos = s - kMaxCopy3Offset;              /* :83 */
@@ -292,6 +300,7 @@ static int64_t encode_l1(uint8_t *dst, const uint8_t *src, int n, int tableBits,
 
             /* repeat check at s+1, :94-145 */
             if ((uint32_t)(cv >> 8) == ld32(src, s - repeat + 1)) {
+                STAT(1);
                 int base = s + 1;
                 for (int i = base - repeat; base > nextEmit && i > 0 && src[i - 1] == src[base - 1];) {
                     i--;
@@ -312,19 +321,22 @@ static int64_t encode_l1(uint8_t *dst, const uint8_t *src, int n, int tableBits,
                 continue;
             }
 
-            if (candidate >= minSrcPos && (uint32_t)cv == ld32(src, candidate)) break; /* :147 */
+            if (candidate >= minSrcPos && (uint32_t)cv == ld32(src, candidate)) { STAT(2); break; } /* :147 */
             candidate = (int)table[hash2];                                               /* :150 */
             if (candidate2 >= minSrcPos && (uint32_t)(cv >> 8) == ld32(src, candidate2)) {
                 table[hash2] = (uint32_t)(s + 2);
                 candidate = candidate2;
                 s++;
+                STAT(3);
                 break;
             }
             table[hash2] = (uint32_t)(s + 2); /* :157 */
             if (candidate >= minSrcPos && (uint32_t)(cv >> 16) == ld32(src, candidate)) {
                 s += 2;
+                STAT(4);
                 break;
             }
+            STAT(5);
             cv = ld64(src, nextS); /* :163 */
             s = nextS;
         }
@@ -372,7 +384,9 @@ static int64_t encode_l1(uint8_t *dst, const uint8_t *src, int n, int tableBits,
             candidate = (int)table[currHash];
             table[m2Hash] = (uint32_t)(s - 2);
             table[currHash] = (uint32_t)s;
+            STAT(6);
             if (s - candidate > kMaxCopy3Offset || (uint32_t)x != ld32(src, candidate)) { /* :242 */
+                STAT(7);
                 cv = ld64(src, s + 1);
                 s++;
                 break;
