@@ -42,12 +42,23 @@ int fail(int code, const char *fmt, ...) {
 constexpr int kMaxDevices = 64;
 constexpr int kCounterSlots = 1024;
 
+// Scratch for one encode launch: the per-warp match tables.  A slice may be
+// reused once the launch that used it has finished (event query).
+struct TableWs {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+};
+
 struct DeviceState {
     std::once_flag once;
     cudaError_t init_err = cudaSuccess;
     int num_sms = 0;
+    int enc_l1_ctas_per_sm = 1;
     int *counters = nullptr;  // kCounterSlots ints
     std::atomic<unsigned> next_counter{0};
+    std::mutex ws_mu;
+    std::vector<TableWs> table_ws;
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -65,7 +76,9 @@ int init_device(int device) {
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, device);
         if (e == cudaSuccess) e = cudaMalloc(&st.counters, kCounterSlots * sizeof(int));
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mz::encode_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.enc_l1_ctas_per_sm, mz::encode_l1_kernel,
+                                                              mz::kEncL1Warps * 32, 0);
+        if (st.enc_l1_ctas_per_sm < 1) st.enc_l1_ctas_per_sm = 1;
         st.init_err = e;
     });
     if (st.init_err != cudaSuccess)
@@ -86,6 +99,32 @@ int launch_decode(int device, int nblk, const uint8_t *src, const uint64_t *sbeg
     return MZCU_OK;
 }
 
+int acquire_tables(DeviceState &st, size_t bytes, TableWs *out) {
+    {
+        std::lock_guard<std::mutex> lk(st.ws_mu);
+        for (size_t i = 0; i < st.table_ws.size(); i++) {
+            TableWs &w = st.table_ws[i];
+            if (w.bytes >= bytes && cudaEventQuery(w.done) == cudaSuccess) {
+                *out = w;
+                st.table_ws.erase(st.table_ws.begin() + i);
+                return MZCU_OK;
+            }
+        }
+        cudaGetLastError();  // clear cudaErrorNotReady from the queries
+    }
+    TableWs w;
+    CU_TRY(cudaMalloc(&w.ptr, bytes));
+    w.bytes = bytes;
+    CU_TRY(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    *out = w;
+    return MZCU_OK;
+}
+
+void release_tables(DeviceState &st, const TableWs &w) {
+    std::lock_guard<std::mutex> lk(st.ws_mu);
+    st.table_ws.push_back(w);
+}
+
 int launch_encode(int device, int level, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send,
                   uint8_t *dst, const uint64_t *dbeg, uint32_t *out_len, cudaStream_t stream) {
     if (nblk == 0) return MZCU_OK;
@@ -93,8 +132,19 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
     int *counter = st.counters + (st.next_counter.fetch_add(1) % kCounterSlots);
     CU_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
     if (level == MZCU_LEVEL_FASTEST) {
-        int grid = nblk < st.num_sms ? nblk : st.num_sms;
-        mz::encode_l1_kernel<<<grid, 32, 128 << 10, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len, counter);
+        // one block per warp, all resident: grid = min(blocks, what fits on the chip)
+        int grid = (nblk + mz::kEncL1Warps - 1) / mz::kEncL1Warps;
+        int resident = st.num_sms * st.enc_l1_ctas_per_sm;
+        if (grid > resident) grid = resident;
+        TableWs ws;
+        int rc = acquire_tables(st, (size_t)grid * mz::kEncL1Warps * mz::kEncL1WsBytesPerWarp, &ws);
+        if (rc) return rc;
+        mz::encode_l1_kernel<<<grid, mz::kEncL1Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len, counter,
+                                                                       static_cast<mz::Slot *>(ws.ptr));
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(ws.done, stream);
+        release_tables(st, ws);
+        if (e != cudaSuccess) return fail(MZCU_ERR_CUDA, "encode_l1 launch: %s", cudaGetErrorString(e));
     } else {
         return fail(MZCU_ERR_INVALID_LEVEL, "level %d not implemented on device", level);
     }

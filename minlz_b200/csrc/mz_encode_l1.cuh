@@ -5,9 +5,29 @@
 // Byte-identical to the pure-Go path: same hash (hash6/15 bit, hash5/13 bit
 // for <= 64 KiB), same probe order, same skip rule, same emit rules.
 //
-// Mapping: one block per CTA, the match table in shared memory (128 KiB for
-// the 15-bit table, so one CTA per SM), the hash walk kept warp-uniform in
-// warp 0 with the 32 lanes sharing match extension and literal copies.
+// Why it looks the way it does
+// ----------------------------
+// The hash walk is one serial dependency chain per block (probe -> verify ->
+// extend -> next position), so the kernel is bound by memory LATENCY, not by
+// bytes per instruction.  Throughput = chains in flight / round trips per
+// step.  Hence:
+//   * one block per WARP and every block of the batch in flight at once
+//     (28+ warps per SM x 148 SMs >= 4096 blocks); shared-memory tables would
+//     cap the chip at ~148 chains.
+//   * the match table lives in a global-memory workspace, and every slot is a
+//     32-byte (one DRAM sector) record {position, 4 bytes before it, 24 bytes
+//     from it}.  A probe then returns the candidate AND the bytes needed to
+//     verify, back-extend (<= 4) and forward-extend (<= 24) it in ONE round
+//     trip; the reference needs table -> src[candidate] -> extend.  The record
+//     is a snapshot of immutable source bytes, so results are unchanged.  This
+//     spends HBM capacity (1 MiB per in-flight block) to buy latency.
+//   * the lanes of the warp evaluate the next few steps of the walk
+//     speculatively in the same round trip: the re-match probe at a match end
+//     plus the search steps that follow if it misses.  Results are then
+//     resolved in the reference's serial order, with in-flight inserts
+//     forwarded between lanes (match.any on the slot index), and only the
+//     inserts of steps that really executed are written back.
+//   * source bytes near the cursor sit in a 1 KiB per-warp shared-memory ring.
 #pragma once
 
 #include "mz_common.cuh"
@@ -16,17 +36,22 @@ namespace mz {
 
 // Forward match extension, restating the Go loop
 //   for s <= limit { if diff := load64(s)^load64(cand); diff != 0 { s += tz>>3; break }; s += 8; cand += 8 }
-// with 32 lanes comparing 32 consecutive 8-byte words per round.
+// with the lanes comparing consecutive 8-byte words; the first round uses 4
+// lanes (most matches end within 32 bytes, and the candidate side is a random
+// DRAM sector), later rounds all 32.
 __device__ __forceinline__ int extend_forward8(const uint8_t *src, int s, int cand, int limit, int lane) {
+    int width = 4;
     for (;;) {
         int pos = s + 8 * lane;
+        const bool act = lane < width;
         bool past = pos > limit;
         uint64_t diff = 0;
-        if (!past) diff = ldg_u64_unaligned(src + pos) ^ ldg_u64_unaligned(src + cand + 8 * lane);
-        unsigned stop = __ballot_sync(kFullMask, past || diff != 0);
+        if (act && !past) diff = ldg_u64_unaligned(src + pos) ^ ldg_u64_unaligned(src + cand + 8 * lane);
+        unsigned stop = __ballot_sync(kFullMask, act && (past || diff != 0));
         if (stop == 0) {
-            s += 256;
-            cand += 256;
+            s += 8 * width;
+            cand += 8 * width;
+            width = 32;
             continue;
         }
         int f = __ffs(stop) - 1;
@@ -101,128 +126,364 @@ struct L1Params {
     }
 };
 
-// Encodes one block with one warp.  `table` is (1 << kTableBits) zeroed u32
-// in shared memory.  Returns bytes written or 0 (not compressible).
+// Backward extension, restating
+//   for cand > 0 && s > floor && src[cand-1] == src[s-1] { cand--; s-- }
+// with one byte pair per lane per round.  Returns the number of steps taken.
+__device__ __forceinline__ int extend_backward(const uint8_t *src, int cand, int s, int floor_, int lane) {
+    int total = 0;
+    for (;;) {
+        int room = min(cand, s - floor_);
+        bool ok = lane < room && src[cand - 1 - lane] == src[s - 1 - lane];
+        unsigned m = __ballot_sync(kFullMask, ok);
+        int cnt = m == kFullMask ? 32 : __ffs(~m) - 1;
+        total += cnt;
+        if (cnt < 32) return total;
+        cand -= 32;
+        s -= 32;
+    }
+}
+
+// ---- table slot record (one 32-byte DRAM sector) ----------------------------
+// a.x = position, a.y = src[pos-4 .. pos), a.z .. b.w = src[pos .. pos+24)
+struct __align__(32) Slot {
+    uint4 a, b;
+};
+constexpr int kSnapFwd = 24;  // forward bytes held in a slot
+
+// ---- per-warp ring of source bytes around the cursor ------------------------
+constexpr int kRingBytes = 1024;
+constexpr int kRingWords = kRingBytes / 4;
+constexpr int kRingChunk = 256;
+
+struct SrcRing {
+    uint32_t *ring;  // kRingWords words of shared memory owned by this warp
+    const uint8_t *src;
+    int n;
+    int filled;  // chunks up to here are loaded (positions >= n read as 0)
+
+    // Loads 256-byte chunks until `want_end` is covered.  All lanes call.
+    __device__ __forceinline__ void ensure(int want_end, int lane) {
+        while (filled < want_end) {
+            int pos = filled + 8 * lane;
+            uint64_t v = 0;
+            if (pos + 8 <= n) {
+                v = ldg_u64_unaligned(src + pos);
+            } else {
+                for (int i = 0; i < 8; i++)
+                    if (pos + i < n) v |= (uint64_t)src[pos + i] << (8 * i);
+            }
+            __syncwarp();
+            int w = (pos >> 2) & (kRingWords - 1);
+            ring[w] = (uint32_t)v;
+            ring[w + 1] = (uint32_t)(v >> 32);
+            filled += kRingChunk;
+            __syncwarp();
+        }
+    }
+
+    // After a long match the cursor may have left the window: restart behind it.
+    __device__ __forceinline__ void seek(int lo) {
+        if (lo >= filled) filled = lo & ~(kRingChunk - 1);
+    }
+
+    // out[0..8) = src[b .. b+32) (b may be negative at the very start of a
+    // block; those bytes are never used).
+    __device__ __forceinline__ void fetch32(int b, uint32_t out[8]) const {
+        int a = b >> 2;
+        unsigned sh = (unsigned)(b & 3) * 8;
+        uint32_t w[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) w[j] = ring[(a + j) & (kRingWords - 1)];
+#pragma unroll
+        for (int j = 0; j < 8; j++) out[j] = __funnelshift_r(w[j], w[j + 1], sh);
+    }
+};
+
+// bytes of common prefix of two 24-byte strings held as 6 words each
+__device__ __forceinline__ int prefix24(const uint32_t *x, const uint32_t *y) {
+    int r = 24;
+#pragma unroll
+    for (int j = 5; j >= 0; j--) {
+        uint32_t d = x[j] ^ y[j];
+        if (d) r = 4 * j + ((__ffs(d) - 1) >> 3);
+    }
+    return r;
+}
+
+constexpr int kEncL1Warps = 4;  // warps per CTA
+constexpr int kEncL1SlotsPerWarp = 1 << 15;
+constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot);  // 1 MiB
+
+// Speculative search steps evaluated per round trip.
+constexpr int kSpecAfterRematch = 1;  // behind a re-match probe
+constexpr int kSpecSearch = 2;        // in a pure search batch
+constexpr int kMaxLevels = 2;
+
+__device__ __forceinline__ int pick(const int (&t)[kMaxLevels + 1], int i) {
+    int r = t[0];
+#pragma unroll
+    for (int j = 1; j <= kMaxLevels; j++) r = i == j ? t[j] : r;
+    return r;
+}
+
+// Encodes one block with one warp.  Returns bytes written or 0.
 template <bool kSmall>
-__device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, int n, uint32_t *table, int lane) {
+__device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Slot *table, uint32_t *ring_mem,
+                               const int lane) {
     using P = L1Params<kSmall>;
     const int sLimit = n - kInputMargin;
     const int dstLimit = n - (n >> 5) - 6;
+    const int fill_limit = (n + 64 + kRingChunk - 1) & ~(kRingChunk - 1);
+
+    SrcRing ring{ring_mem, src, n, 0};
+    ring.ensure(min(2 * kRingChunk, fill_limit), lane);
+
+    // Empty slots read as candidate 0 (encode_l1.go:52,86): position 0 and its bytes.
+    {
+        uint32_t w0[8];
+        ring.fetch32(-4, w0);
+        const uint4 ia = make_uint4(0, 0, w0[1], w0[2]);
+        const uint4 ib = make_uint4(w0[3], w0[4], w0[5], w0[6]);
+        const int slots = 1 << P::kTableBits;
+        for (int i = lane; i < slots; i += 32) {
+            uint4 *q = reinterpret_cast<uint4 *>(table + i);
+            q[0] = ia;
+            q[1] = ib;
+        }
+        __syncwarp();
+    }
+
     int nextEmit = 0;
     int s = 1;
-    uint64_t cv = ldg_u64_unaligned(src + s);
     int repeat = 1;
     int d = 0;
-    int candidate;
+    bool rematch = false;  // the next batch starts with the re-match probe at s (:222-265)
 
     for (;;) {
-        candidate = 0;
-        for (;;) {
-            int nextS = s + ((s - nextEmit) >> P::kSkipLog) + 4;
-            if (nextS > sLimit) goto emit_remainder;
-            int minSrcPos = s - kMaxCopy3Offset;
-            uint32_t hash0 = P::hash(cv);
-            uint32_t hash1 = P::hash(cv >> 8);
-            candidate = (int)table[hash0];
-            int candidate2 = (int)table[hash1];
-            __syncwarp();
-            if (lane == 0) {
-                table[hash0] = (uint32_t)s;
-                table[hash1] = (uint32_t)(s + 1);
-            }
-            __syncwarp();
-            uint32_t hash2 = P::hash(cv >> 16);
-
-            if ((uint32_t)(cv >> 8) == ldg_u32_unaligned(src + s - repeat + 1)) {
-                int base = s + 1;
-                for (int i = base - repeat; base > nextEmit && i > 0 && src[i - 1] == src[base - 1];) {
-                    i--;
-                    base--;
+        // ---------------- plan the batch ----------------
+        if (rematch) {
+            nextEmit = s;
+            if (s >= sLimit) break;
+            if (d > dstLimit) return 0;
+        }
+        const int ne = nextEmit;
+        ring.seek(s - 8);
+        ring.ensure(min(s + 320, fill_limit), lane);
+        // level j probes t[j], t[j]+1, t[j]+2; t[j+1] is its nextS (:79)
+        int t[kMaxLevels + 1];
+        t[0] = rematch ? s + 1 : s;
+        int nlev = 0;
+        bool hit_end = false;  // the first level not probed starts with nextS > sLimit (:80)
+        {
+            const int want = rematch ? kSpecAfterRematch : kSpecSearch;
+            bool open = true;
+#pragma unroll
+            for (int j = 0; j < kMaxLevels; j++) {
+                int nxt = t[j] + ((t[j] - ne) >> P::kSkipLog) + 4;
+                t[j + 1] = nxt;
+                if (open && j < want) {
+                    if (nxt > sLimit) {
+                        hit_end = true;
+                        open = false;
+                    } else if (t[j] + 2 + 28 <= ring.filled) {
+                        nlev = j + 1;
+                    } else {
+                        open = false;
+                    }
+                } else {
+                    open = false;
                 }
-                if (d + (base - nextEmit) > dstLimit) return 0;
-                d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane);
-                int cand = s - repeat + 4 + 1;
-                s += 4 + 1;
-                s = extend_forward8(src, s, cand, sLimit, lane);
-                d += emit_repeat(dst + d, s - base, lane);
-                nextEmit = s;
-                if (s >= sLimit) goto emit_remainder;
-                cv = ldg_u64_unaligned(src + s);
-                continue;
             }
-
-            if (candidate >= minSrcPos && (uint32_t)cv == ldg_u32_unaligned(src + candidate)) break;
-            candidate = (int)table[hash2];
-            __syncwarp();
-            if (lane == 0) table[hash2] = (uint32_t)(s + 2);
-            __syncwarp();
-            if (candidate2 >= minSrcPos && (uint32_t)(cv >> 8) == ldg_u32_unaligned(src + candidate2)) {
-                candidate = candidate2;
-                s++;
-                break;
-            }
-            if (candidate >= minSrcPos && (uint32_t)(cv >> 16) == ldg_u32_unaligned(src + candidate)) {
-                s += 2;
-                break;
-            }
-            cv = ldg_u64_unaligned(src + nextS);
-            s = nextS;
+        }
+        if (!rematch && nlev == 0) {
+            if (hit_end) break;
+            return 0;  // unreachable: ensure() always covers one level
         }
 
-        while (candidate > 0 && s > nextEmit && src[candidate - 1] == src[s - 1]) {
-            candidate--;
-            s--;
+        // ---------------- lane roles ----------------
+        // lane 0: insert-only (s-2)      lane 1: re-match probe (s)
+        // lanes 2+4j .. 5+4j: level j -> hash0(t), hash1(t+1), hash2(t+2), repeat probe at t+1
+        int lvl = -1, sub = 0, p = 0;
+        if (lane < 2) {
+            if (rematch) {
+                lvl = -2;
+                p = lane == 0 ? s - 2 : s;
+            }
+        } else if (lane < 2 + 4 * kMaxLevels) {
+            const int j = (lane - 2) >> 2;
+            sub = (lane - 2) & 3;
+            if (j < nlev) {
+                lvl = j;
+                p = pick(t, j) + (sub == 3 ? 1 : sub);
+            }
         }
-        int base = s;
-        repeat = base - candidate;
-        s += 4;
-        candidate += 4;
-        s = extend_forward8(src, s, candidate, n - 8, lane);
-        int length = s - base;
-        if (nextEmit != base) {
-            if (base - nextEmit > P::kMaxFuseLits || repeat < kMinCopy2Offset) {
-                if (d + (s - nextEmit) > dstLimit) return 0;
-                d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane);
+        const bool active = lvl != -1;
+        const bool isrep = lvl >= 0 && sub == 3;
+        const bool inserts = active && !isrep;
+        const bool reads = inserts && !(lvl == -2 && lane == 0);
+
+        uint32_t W[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // src[p-4 .. p+28)
+        if (active) ring.fetch32(p - 4, W);
+        const uint32_t h = P::hash((uint64_t)W[2] << 32 | W[1]);
+
+        // one 32-byte sector per probing lane; the repeat probe reads the source
+        uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
+        if (reads) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(table + h);
+            ea = q[0];
+            eb = q[1];
+        }
+        uint32_t rep4 = 0;
+        if (isrep) rep4 = ldg_u32_unaligned(src + p - repeat);
+
+        // in-flight forwarding: the latest earlier insert (serial order = lane order) on my slot
+        const unsigned ins_mask = __ballot_sync(kFullMask, inserts);
+        const unsigned same = __match_any_sync(kFullMask, inserts ? h : 0x80000000u + lane) & ins_mask;
+        unsigned vis = 0;
+        if (reads && lvl >= 0) {
+            vis = (1u << (2 + 4 * lvl)) - 1;           // the re-match lanes and every earlier level
+            if (sub == 2) vis |= 3u << (2 + 4 * lvl);  // hash2 is read after hash0/hash1 were written
+            vis &= same;
+        }
+        int cand = (int)ea.x;
+        uint32_t cb = ea.y;
+        uint32_t cd[6] = {ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+        const bool fwd = vis != 0;
+        if (__any_sync(kFullMask, fwd)) {  // rare: short-period data
+            const int from = fwd ? 31 - __clz(vis) : lane;
+            const int cpos = __shfl_sync(kFullMask, p, from);
+            if (fwd) {
+                cand = cpos;
+                uint32_t V[8];
+                ring.fetch32(cand - 4, V);
+                cb = V[0];
+#pragma unroll
+                for (int j = 0; j < 6; j++) cd[j] = V[j + 1];
+            }
+        }
+
+        // ---------------- evaluate ----------------
+        bool ok = false;
+        int fbytes = 0, bbytes = 0;
+        if (reads) {
+            const int anchor = lvl >= 0 ? pick(t, lvl) : s;
+            const bool in_range = lvl >= 0 ? cand >= anchor - kMaxCopy3Offset : s - cand <= kMaxCopy3Offset;
+            if (in_range && cd[0] == W[1]) {
+                ok = true;
+                fbytes = prefix24(cd, W + 1);
+                const uint32_t x = cb ^ W[0];
+                bbytes = x ? __clz(x) >> 3 : 4;
+            }
+        } else if (isrep) {
+            ok = rep4 == W[1];
+        }
+        const unsigned okm = __ballot_sync(kFullMask, ok);
+
+        // serial priority: re-match probe; then per level repeat, hash0, hash1, hash2
+        int win = -1;
+        int win_lvl = nlev;  // nlev: every probed level missed
+        if (rematch && (okm & 2u)) {
+            win = 1;
+            win_lvl = -2;
+        } else {
+#pragma unroll
+            for (int j = kMaxLevels - 1; j >= 0; j--) {
+                const unsigned g = (okm >> (2 + 4 * j)) & 15u;
+                if (j < nlev && g) {
+                    win = 2 + 4 * j + ((g & 8u) ? 3 : (g & 1u) ? 0 : (g & 2u) ? 1 : 2);
+                    win_lvl = j;
+                }
+            }
+        }
+        const int wsub = win >= 2 ? (win - 2) & 3 : 0;
+
+        // ---------------- write back the inserts that really happened ----------------
+        {
+            bool w = false;
+            if (inserts) {
+                if (lvl == -2) w = true;                       // :238-239 run before the test
+                else if (win_lvl == -2) w = false;
+                else if (lvl < win_lvl) w = true;
+                else if (lvl == win_lvl) w = sub < 2 || wsub == 1 || wsub == 2;  // hash2: :152/:157 only
+            }
+            const unsigned wm = __ballot_sync(kFullMask, w);
+            if (w && (same & wm & ~((2u << lane) - 1u)) == 0) {  // a later insert on the same slot wins
+                uint4 *q = reinterpret_cast<uint4 *>(table + h);
+                q[0] = make_uint4((uint32_t)p, W[0], W[1], W[2]);
+                q[1] = make_uint4(W[3], W[4], W[5], W[6]);
+            }
+            __syncwarp();
+        }
+
+        if (win < 0) {  // every probed step missed: continue the search behind them
+            s = pick(t, nlev);
+            rematch = false;
+            if (hit_end) break;
+            continue;
+        }
+
+        // ---------------- process the hit ----------------
+        const int wcand = __shfl_sync(kFullMask, cand, win);
+        const int wf = __shfl_sync(kFullMask, fbytes, win);
+        const int wb = __shfl_sync(kFullMask, bbytes, win);
+
+        if (win_lvl >= 0 && wsub == 3) {  // repeat at t+1 (encode_l1.go:94-145)
+            const int tt = pick(t, win_lvl);
+            int base = tt + 1;
+            base -= extend_backward(src, base - repeat, base, ne, lane);
+            if (d + (base - ne) > dstLimit) return 0;
+            d += emit_literal(dst + d, src + ne, base - ne, lane);
+            s = extend_forward8(src, tt + 5, tt + 5 - repeat, sLimit, lane);
+            d += emit_repeat(dst + d, s - base, lane);
+            nextEmit = s;
+            if (s >= sLimit) break;
+            rematch = false;
+            continue;
+        }
+
+        int base, known;  // match start, bytes known equal from it
+        if (win_lvl == -2) {
+            base = s;
+            repeat = s - wcand;
+            known = wf;
+        } else {
+            const int ps = pick(t, win_lvl) + wsub;
+            const int room = min(wcand, ps - ne);  // :169-172
+            int back = min(wb, room);
+            if (back == 4 && room > 4) back += extend_backward(src, wcand - 4, ps - 4, ne, lane);
+            base = ps - back;
+            repeat = ps - wcand;
+            known = back + wf;
+        }
+        {
+            // Go: s = base+4, then 8-byte chunks while s <= n-8 (:181-188)
+            int q_stop = base + 4;
+            if (q_stop <= n - 8) q_stop += ((n - 8 - q_stop) / 8 + 1) * 8;
+            if (wf < kSnapFwd) {
+                s = min(base + known, q_stop);
+            } else {
+                const int sc = base + 4 + 8 * ((known - 4) >> 3);
+                s = min(extend_forward8(src, sc, sc - repeat, n - 8, lane), q_stop);
+            }
+        }
+        const int length = s - base;
+        if (win_lvl != -2 && ne != base) {
+            if (base - ne > P::kMaxFuseLits || repeat < kMinCopy2Offset) {
+                if (d + (s - ne) > dstLimit) return 0;
+                d += emit_literal(dst + d, src + ne, base - ne, lane);
                 d += emit_copy(dst + d, repeat, length, lane);
             } else if (repeat <= kMaxCopy2Offset) {
-                d += emit_copy_lits2(dst + d, src + nextEmit, base - nextEmit, repeat, length, lane);
+                d += emit_copy_lits2(dst + d, src + ne, base - ne, repeat, length, lane);
             } else {
-                d += emit_copy_lits3(dst + d, src + nextEmit, base - nextEmit, repeat, length, lane);
+                d += emit_copy_lits3(dst + d, src + ne, base - ne, repeat, length, lane);
             }
         } else {
             d += emit_copy(dst + d, repeat, length, lane);
         }
-
-        for (;;) {
-            nextEmit = s;
-            if (s >= sLimit) goto emit_remainder;
-            uint64_t x = ldg_u64_unaligned(src + s - 2);
-            if (d > dstLimit) return 0;
-            uint32_t m2Hash = P::hash(x);
-            x >>= 16;
-            uint32_t currHash = P::hash(x);
-            candidate = (int)table[currHash];
-            __syncwarp();
-            if (lane == 0) {
-                table[m2Hash] = (uint32_t)(s - 2);
-                table[currHash] = (uint32_t)s;
-            }
-            __syncwarp();
-            if (s - candidate > kMaxCopy3Offset || (uint32_t)x != ldg_u32_unaligned(src + candidate)) {
-                cv = ldg_u64_unaligned(src + s + 1);
-                s++;
-                break;
-            }
-            repeat = s - candidate;
-            base = s;
-            s += 4;
-            candidate += 4;
-            s = extend_forward8(src, s, candidate, n - 8, lane);
-            d += emit_copy(dst + d, repeat, s - base, lane);
-        }
+        rematch = true;
     }
 
-emit_remainder:
+    // emitRemainder (encode_l1.go:268-282)
     if (nextEmit < n) {
         if (d + n - nextEmit > dstLimit) return 0;
         d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane);
@@ -230,13 +491,17 @@ emit_remainder:
     return d;
 }
 
-// Persistent kernel: CTAs pull block indices from *counter.
-__global__ void __launch_bounds__(32)
+// Persistent kernel: every warp pulls block indices from *counter and owns the
+// workspace slice `tables + global_warp * 1 MiB`.
+__global__ void __launch_bounds__(kEncL1Warps * 32)
 encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
-                 uint32_t *__restrict__ out_len, int *counter) {
-    extern __shared__ __align__(16) uint32_t table[];
+                 uint32_t *__restrict__ out_len, int *counter, Slot *tables) {
+    __shared__ uint32_t rings[kEncL1Warps][kRingWords];
     const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int gwarp = blockIdx.x * kEncL1Warps + warp;
+    Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(counter, 1);
@@ -248,12 +513,8 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
         int res = 0;
         if (n64 >= kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {
             const int n = (int)n64;
-            const bool small = n <= 65536;
-            const int words = small ? (1 << 13) : (1 << 15);
-            uint4 *t4 = reinterpret_cast<uint4 *>(table);
-            for (int i = lane; i < words / 4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-            res = small ? encode_l1_block<true>(dp, sp, n, table, lane) : encode_l1_block<false>(dp, sp, n, table, lane);
+            res = n <= 65536 ? encode_l1_block<true>(dp, sp, n, table, rings[warp], lane)
+                             : encode_l1_block<false>(dp, sp, n, table, rings[warp], lane);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
