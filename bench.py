@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--block-size", type=int, default=1 << 20)
     ap.add_argument("--kind", default="json")
     ap.add_argument("--cpu-blocks", type=int, default=1024, help="bounded sample for the CPU legs")
-    ap.add_argument("--e2e-blocks", type=int, default=1024, help="blocks per e2e step (host buffers)")
+    ap.add_argument("--e2e-blocks", type=int, default=4096, help="blocks per e2e step (host buffers)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -292,24 +292,18 @@ def main():
         nb = min(nblk, args.e2e_blocks)
         h_src = torch.empty(nb * bs, dtype=torch.uint8).pin_memory()
         h_src.copy_(src[: nb * bs])
-        h_enc = torch.empty(nb * cap, dtype=torch.uint8).pin_memory()
         h_dec = torch.empty(nb * bs, dtype=torch.uint8).pin_memory()
         h_comp = torch.empty(nb * bs, dtype=torch.uint8).pin_memory()
-        n_src, n_enc, n_dec, n_comp = h_src.numpy(), h_enc.numpy(), h_dec.numpy(), h_comp.numpy()
+        n_src, n_dec, n_comp = h_src.numpy(), h_dec.numpy(), h_comp.numpy()
         hs = np.arange(nb + 1, dtype=np.uint64) * bs
-        he = np.arange(nb + 1, dtype=np.uint64) * cap
-        hlen = np.zeros(nb, dtype=np.uint32)
+        hc = np.zeros(nb + 1, dtype=np.uint64)
         hst = np.zeros(nb, dtype=np.int32)
 
         def e2e_step():
-            mz.encode_blocks_into(n_src, hs, n_enc, he, hlen, mz.LevelFastest, device=local)
-            hc = np.zeros(nb + 1, dtype=np.uint64)
-            np.cumsum(hlen, out=hc[1:])
-            # host-side hand-off of the compressed blocks (what a Writer does)
-            for i in range(nb):
-                n_comp[int(hc[i]):int(hc[i + 1])] = n_enc[int(he[i]):int(he[i]) + int(hlen[i])]
+            # host blocks -> packed token streams on the host -> host blocks again
+            cb_ = mz.encode_blocks_packed_into(n_src, hs, n_comp, hc, mz.LevelFastest, device=local)
             mz.decode_blocks_into(n_comp, hc, n_dec, hs, hst, device=local)
-            return int(hc[-1])
+            return cb_
 
         for _ in range(min(args.warmup, 2)):
             e2e_step()
@@ -330,7 +324,7 @@ def main():
                "h2d_bytes_per_step": int(nb * bs + cb + 2 * 8 * (nb + 1) * 2),
                "d2h_bytes_per_step": int(cb + nb * bs + 8 * nb),
                "blocks_per_step": nb, "ms_per_step": round(dt * 1e3, 3),
-               "api": "mzcu_encode_blocks + mzcu_decode_blocks (host pointers, pinned)"}
+               "api": "mzcu_encode_blocks_packed + mzcu_decode_blocks (host pointers, pinned)"}
 
     if rank != 0:
         if dist is not None:

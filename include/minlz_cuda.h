@@ -113,6 +113,13 @@ int mzcu_encode_blocks(int device, int level, int nblk, const uint8_t *src, cons
                        const uint64_t *dst_off, uint32_t *out_len);
 int mzcu_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                        const uint64_t *dst_off, int32_t *status);
+/* Like mzcu_encode_blocks, but the token streams are written back to back:
+ * block i occupies dst[dst_off_out[i] .. dst_off_out[i+1]) (dst_off_out has
+ * nblk+1 entries and is an OUTPUT); an empty range means "not compressible".
+ * One D2H copy for the whole batch; the result feeds mzcu_decode_blocks as is.
+ * dst_cap >= sum of source lengths is always enough. */
+int mzcu_encode_blocks_packed(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
+                              uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out);
 
 /* ---- block API level (full blocks with header), host pointers ----------
  *

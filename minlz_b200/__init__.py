@@ -313,6 +313,17 @@ def encode_blocks_into(src, src_off, dst, dst_off, out_len, level, device=-1):
         _raise(r)
 
 
+def encode_blocks_packed_into(src, src_off, dst, dst_off_out, level, device=-1):
+    """Host numpy buffers; token streams packed back to back into dst, offsets
+    (uint64, nblk+1) written to dst_off_out.  Returns the packed size."""
+    nblk = len(src_off) - 1
+    r = _lib.load().mzcu_encode_blocks_packed(device, level, nblk, src.ctypes.data, src_off.ctypes.data, dst.ctypes.data,
+                                              dst.size, dst_off_out.ctypes.data)
+    if r < 0:
+        _raise(r)
+    return int(dst_off_out[nblk])
+
+
 def decode_blocks_into(src, src_off, dst, dst_off, status, device=-1):
     nblk = len(src_off) - 1
     r = _lib.load().mzcu_decode_blocks(device, nblk, src.ctypes.data, src_off.ctypes.data, dst.ctypes.data,

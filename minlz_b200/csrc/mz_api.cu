@@ -392,6 +392,65 @@ int host_encode_blocks(int device, int level, int nblk, const uint8_t *src, cons
     return MZCU_OK;
 }
 
+// Seam-level encode for host buffers with dense output: the token streams are
+// packed back to back on the device and leave with one D2H copy.
+int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                              size_t dst_cap, uint64_t *dst_off_out) {
+    if (nblk < 0 || !dst_off_out || (nblk > 0 && (!src_off || !dst))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+        return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
+    dst_off_out[0] = 0;
+    if (nblk == 0) return MZCU_OK;
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    WsGuard g;
+    rc = ws_acquire(device, &g.w);
+    if (rc) return rc;
+    Workspace *w = g.w;
+    size_t dst_bytes = 0;
+    for (int i = 0; i < nblk; i++) {
+        if (src_off[i + 1] < src_off[i]) return fail(MZCU_ERR_INVALID_ARG, "offsets not monotonic");
+        size_t n = src_off[i + 1] - src_off[i];
+        if (n > MZCU_MAX_BLOCK_SIZE) return fail(MZCU_ERR_TOO_LARGE, "block %d larger than 8 MiB", i);
+        dst_bytes += (n + 2 + 15) & ~size_t(15);
+    }
+    const size_t base = src_off[0];
+    const size_t total = src_off[nblk] - base;
+    rc = ws_reserve(w, total, dst_bytes, (size_t)nblk);
+    if (rc) return rc;
+    const size_t T = w->cap_tab;
+    uint64_t *h_sbeg = w->h_tab, *h_send = w->h_tab + T, *h_dbeg = w->h_tab + 2 * T, *h_poff = w->h_tab + 3 * T;
+    uint64_t *d_sbeg = w->d_tab, *d_send = w->d_tab + T, *d_dbeg = w->d_tab + 2 * T, *d_poff = w->d_tab + 3 * T;
+    uint32_t *d_out = reinterpret_cast<uint32_t *>(w->d_tab + 4 * T);
+    size_t dof = 0;
+    for (int i = 0; i < nblk; i++) {
+        h_sbeg[i] = src_off[i] - base;
+        h_send[i] = src_off[i + 1] - base;
+        h_dbeg[i] = dof;
+        dof += (src_off[i + 1] - src_off[i] + 2 + 15) & ~size_t(15);
+    }
+    if (total) CU_TRY(cudaMemcpyAsync(w->d_src, src + base, total, cudaMemcpyHostToDevice, w->stream));
+    CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 3 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+    CU_TRY(cudaEventRecord(w->ev0, w->stream));
+    rc = launch_encode(device, level, nblk, w->d_src, d_sbeg, d_send, w->d_dst, d_dbeg, d_out, w->stream);
+    if (rc) return rc;
+    // the source is dead after the encode: pack into its buffer (sum(len) < total)
+    rc = launch_pack(device, nblk, w->d_dst, d_dbeg, d_out, w->d_src, d_poff, w->stream);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(w->ev1, w->stream));
+    CU_TRY(cudaMemcpyAsync(h_poff, d_poff, (size_t)(nblk + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, w->stream));
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    const size_t packed = h_poff[nblk];
+    if (packed > dst_cap) return fail(MZCU_ERR_DST_TOO_SMALL, "packed output %zu > capacity %zu", packed, dst_cap);
+    if (packed) CU_TRY(cudaMemcpyAsync(dst, w->d_src, packed, cudaMemcpyDeviceToHost, w->stream));
+    for (int i = 0; i <= nblk; i++) dst_off_out[i] = h_poff[i];
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
+    return MZCU_OK;
+}
+
 // Seam-level decode for host buffers.  `sbeg/send` index into `src`.
 int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint8_t *dst,
                        const uint64_t *dbeg, const uint64_t *dend, int32_t *status) {
@@ -536,6 +595,11 @@ int mzcu_pack_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_
 int mzcu_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                        const uint64_t *dst_off, uint32_t *out_len) {
     return host_encode_blocks(device, level, nblk, src, src_off, dst, dst_off, out_len);
+}
+
+int mzcu_encode_blocks_packed(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
+                              uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out) {
+    return host_encode_blocks_packed(device, level, nblk, src, src_off, dst, dst_cap, dst_off_out);
 }
 
 int mzcu_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,

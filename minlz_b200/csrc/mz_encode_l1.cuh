@@ -259,6 +259,20 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
     int d = 0;
     bool rematch = false;  // the next batch starts with the re-match probe at s (:222-265)
 
+    // loop-invariant lane roles
+    // lane 0: insert-only (s-2)      lane 1: re-match probe (s)
+    // lanes 2+4j .. 5+4j: level j -> hash0(t), hash1(t+1), hash2(t+2), repeat probe at t+1
+    const bool lvl_lane = lane >= 2 && lane < 2 + 4 * kMaxLevels;
+    const int my_lvl = (lane - 2) >> 2;
+    const int sub = lvl_lane ? (lane - 2) & 3 : 0;
+    const int padd = sub == 3 ? 1 : sub;
+    unsigned vis_base = 0;
+    if (lvl_lane && sub < 3) {
+        vis_base = (1u << (2 + 4 * my_lvl)) - 1;           // the re-match lanes and every earlier level
+        if (sub == 2) vis_base |= 3u << (2 + 4 * my_lvl);  // hash2 is read after hash0/hash1 were written
+    }
+    const unsigned later = ~((2u << lane) - 1u);
+
     for (;;) {
         // ---------------- plan the batch ----------------
         if (rematch) {
@@ -300,30 +314,22 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             return 0;  // unreachable: ensure() always covers one level
         }
 
-        // ---------------- lane roles ----------------
-        // lane 0: insert-only (s-2)      lane 1: re-match probe (s)
-        // lanes 2+4j .. 5+4j: level j -> hash0(t), hash1(t+1), hash2(t+2), repeat probe at t+1
-        int lvl = -1, sub = 0, p = 0;
+        // ---------------- this batch's lane roles ----------------
+        int lvl = -1, p = s;
         if (lane < 2) {
-            if (rematch) {
-                lvl = -2;
-                p = lane == 0 ? s - 2 : s;
-            }
-        } else if (lane < 2 + 4 * kMaxLevels) {
-            const int j = (lane - 2) >> 2;
-            sub = (lane - 2) & 3;
-            if (j < nlev) {
-                lvl = j;
-                p = pick(t, j) + (sub == 3 ? 1 : sub);
-            }
+            lvl = rematch ? -2 : -1;
+            p = lane == 0 ? s - 2 : s;
+        } else if (lvl_lane && my_lvl < nlev) {
+            lvl = my_lvl;
+            p = pick(t, my_lvl) + padd;
         }
         const bool active = lvl != -1;
         const bool isrep = lvl >= 0 && sub == 3;
         const bool inserts = active && !isrep;
-        const bool reads = inserts && !(lvl == -2 && lane == 0);
+        const bool reads = inserts && lane != 0;
 
-        uint32_t W[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // src[p-4 .. p+28)
-        if (active) ring.fetch32(p - 4, W);
+        uint32_t W[8];  // src[p-4 .. p+28)
+        ring.fetch32(p - 4, W);
         const uint32_t h = P::hash((uint64_t)W[2] << 32 | W[1]);
 
         // one 32-byte sector per probing lane; the repeat probe reads the source
@@ -339,12 +345,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         // in-flight forwarding: the latest earlier insert (serial order = lane order) on my slot
         const unsigned ins_mask = __ballot_sync(kFullMask, inserts);
         const unsigned same = __match_any_sync(kFullMask, inserts ? h : 0x80000000u + lane) & ins_mask;
-        unsigned vis = 0;
-        if (reads && lvl >= 0) {
-            vis = (1u << (2 + 4 * lvl)) - 1;           // the re-match lanes and every earlier level
-            if (sub == 2) vis |= 3u << (2 + 4 * lvl);  // hash2 is read after hash0/hash1 were written
-            vis &= same;
-        }
+        const unsigned vis = reads ? vis_base & same : 0;
         int cand = (int)ea.x;
         uint32_t cb = ea.y;
         uint32_t cd[6] = {ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
@@ -407,7 +408,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                 else if (lvl == win_lvl) w = sub < 2 || wsub == 1 || wsub == 2;  // hash2: :152/:157 only
             }
             const unsigned wm = __ballot_sync(kFullMask, w);
-            if (w && (same & wm & ~((2u << lane) - 1u)) == 0) {  // a later insert on the same slot wins
+            if (w && (same & wm & later) == 0) {  // a later insert on the same slot wins
                 uint4 *q = reinterpret_cast<uint4 *>(table + h);
                 q[0] = make_uint4((uint32_t)p, W[0], W[1], W[2]);
                 q[1] = make_uint4(W[3], W[4], W[5], W[6]);

@@ -294,3 +294,24 @@ def test_full_size_roundtrip_property():
     torch.cuda.synchronize()
     assert int(status.abs().sum()) == 0
     assert torch.equal(dec, src)
+
+
+def test_encode_packed_host_api(oracle):
+    """mzcu_encode_blocks_packed: dense output + offsets, feeds decode as is."""
+    items = patterns.reference_patterns()[:20] + [("rnd", np.random.default_rng(5).integers(0, 256, 5000, dtype=np.uint8).tobytes())]
+    raws = [d for _, d in items]
+    src, soff = _cat(raws)
+    dst = np.zeros(max(len(src), 1), dtype=np.uint8)
+    poff = np.zeros(len(raws) + 1, dtype=np.uint64)
+    total = mz.encode_blocks_packed_into(src, soff, dst, poff, 1)
+    assert total == int(poff[-1])
+    for i, data in enumerate(raws):
+        want = oracle.encode_block(data, 1)
+        assert dst[int(poff[i]):int(poff[i + 1])].tobytes() == want
+    # blocks the encoder gave up on have empty ranges; decode the rest
+    keep = [i for i in range(len(raws)) if poff[i + 1] > poff[i]]
+    streams = [dst[int(poff[i]):int(poff[i + 1])].tobytes() for i in keep]
+    csrc, csoff = _cat(streams)
+    _, doff = _cat([raws[i] for i in keep])
+    out, status = mz.decode_blocks(csrc, csoff, doff)
+    assert not status.any() and out.tobytes() == b"".join(raws[i] for i in keep)
