@@ -17,6 +17,7 @@
 
 #include "mz_decode.cuh"
 #include "mz_encode_l1.cuh"
+#include "mz_encode_l2.cuh"
 #include "mz_pack.cuh"
 
 namespace {
@@ -55,6 +56,7 @@ struct DeviceState {
     cudaError_t init_err = cudaSuccess;
     int num_sms = 0;
     int enc_l1_ctas_per_sm = 1;
+    int enc_l2_ctas_per_sm = 1;
     int *counters = nullptr;  // kCounterSlots ints
     std::atomic<unsigned> next_counter{0};
     std::mutex ws_mu;
@@ -79,6 +81,10 @@ int init_device(int device) {
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.enc_l1_ctas_per_sm, mz::encode_l1_kernel,
                                                               mz::kEncL1Warps * 32, 0);
         if (st.enc_l1_ctas_per_sm < 1) st.enc_l1_ctas_per_sm = 1;
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.enc_l2_ctas_per_sm, mz::encode_l2_kernel,
+                                                              mz::kEncL2Warps * 32, 0);
+        if (st.enc_l2_ctas_per_sm < 1) st.enc_l2_ctas_per_sm = 1;
         st.init_err = e;
     });
     if (st.init_err != cudaSuccess)
@@ -145,8 +151,21 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
         if (e == cudaSuccess) e = cudaEventRecord(ws.done, stream);
         release_tables(st, ws);
         if (e != cudaSuccess) return fail(MZCU_ERR_CUDA, "encode_l1 launch: %s", cudaGetErrorString(e));
+    } else if (level == MZCU_LEVEL_BALANCED) {
+        int grid = (nblk + mz::kEncL2Warps - 1) / mz::kEncL2Warps;
+        int resident = st.num_sms * st.enc_l2_ctas_per_sm;
+        if (grid > resident) grid = resident;
+        TableWs ws;
+        int rc = acquire_tables(st, (size_t)grid * mz::kEncL2Warps * mz::kEncL2WsBytesPerWarp, &ws);
+        if (rc) return rc;
+        mz::encode_l2_kernel<<<grid, mz::kEncL2Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len, counter,
+                                                                       static_cast<uint32_t *>(ws.ptr));
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(ws.done, stream);
+        release_tables(st, ws);
+        if (e != cudaSuccess) return fail(MZCU_ERR_CUDA, "encode_l2 launch: %s", cudaGetErrorString(e));
     } else {
-        return fail(MZCU_ERR_INVALID_LEVEL, "level %d not implemented on device", level);
+        return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
     }
     CU_TRY(cudaGetLastError());
     return MZCU_OK;

@@ -1,0 +1,297 @@
+// mz_encode_l2.cuh -- MinLZ LevelBalanced block encoder (sm_100a).
+//
+// Replaces encodeBlockBetter (reference asm_none.go:68-76 ->
+// encode_l2.go:61-338 encodeBlockBetterGo and :343-596 ...Go64K; asm twin
+// encodeBetterBlockAsm*).  Byte-identical to the pure-Go path: long table
+// 17 bit / hash7 and short table 14 bit / hash4 (15 bit / hash6 and 12 bit for
+// blocks <= 64 KiB), same probe order (long-8, repeat, long-4, short + long at
+// s+1), same skip rule, same re-indexing of the match interior.
+//
+// Mapping: one block per warp, all blocks of the batch in flight at once; the
+// 576 KiB of tables per block do not fit shared memory (and shared memory
+// would cap the chip at ~148 chains of a latency-bound walk), so they live in
+// a global-memory workspace slice per warp.  Lanes 0-3 issue the independent
+// probes of a step (long, short, repeat, long at s+1) in one round trip; match
+// extension is lane parallel.
+#pragma once
+
+#include "mz_common.cuh"
+#include "mz_encode_l1.cuh"
+
+namespace mz {
+
+template <bool kSmall>
+struct L2Params {
+    static constexpr int kLBits = kSmall ? 15 : 17;
+    static constexpr int kSBits = kSmall ? 12 : 14;
+    __device__ static __forceinline__ uint32_t hashL(uint64_t u) { return kSmall ? hash6(u, kLBits) : hash7(u, kLBits); }
+    __device__ static __forceinline__ uint32_t hashS(uint64_t u) { return hash4(u, kSBits); }
+};
+
+constexpr int kEncL2Warps = 4;
+constexpr size_t kEncL2WsBytesPerWarp = ((size_t)(1 << 17) + (1 << 14)) * 4;  // 576 KiB
+
+// 8 bytes at pos, zero filled past n; never touches a word with no byte < n.
+__device__ __forceinline__ uint64_t ld64_clamped(const uint8_t *src, int pos, int n) {
+    if (pos + 8 <= n) return ldg_u64_unaligned(src + pos);
+    uint64_t v = 0;
+    for (int i = 0; i < 8 && pos + i < n; i++) v |= (uint64_t)src[pos + i] << (8 * i);
+    return v;
+}
+
+// Forward extension with byte tail (encode_l2.go:160-175, :239-254): the
+// common prefix of src[s..n) and src[cand..], 8 bytes per lane per round.
+__device__ __forceinline__ int extend_to_end(const uint8_t *src, int n, int s, int cand, int lane) {
+    int width = 4;
+    for (;;) {
+        const int pos = s + 8 * lane;
+        const bool act = lane < width;
+        uint64_t diff = 0;
+        bool stop = false;
+        if (act) {
+            if (pos >= n) {
+                stop = true;  // nothing left: ends exactly here
+            } else {
+                diff = ld64_clamped(src, pos, n) ^ ld64_clamped(src, cand + 8 * lane, n);
+                const int left = n - pos;
+                if (left < 8) diff |= 1ull << (8 * left);  // the block ends inside this word
+                stop = diff != 0;
+            }
+        }
+        const unsigned m = __ballot_sync(kFullMask, stop);
+        if (m == 0) {
+            s += 8 * width;
+            cand += 8 * width;
+            width = 32;
+            continue;
+        }
+        const int f = __ffs(m) - 1;
+        int add = diff ? (__ffsll((long long)diff) - 1) >> 3 : 0;
+        add = __shfl_sync(kFullMask, add, f);
+        return s + 8 * f + add;
+    }
+}
+
+template <bool kSmall>
+__device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, uint32_t *lTable, uint32_t *sTable,
+                               const int lane) {
+    using P = L2Params<kSmall>;
+    const int sLimit = n - kInputMargin;
+    const int dstLimit = n - (n >> 5) - 6;
+    int nextEmit = 0;
+    int s = 1;
+    uint64_t cv = ldg_u64_unaligned(src + s);
+    int repeat = 1;
+    int d = 0;
+
+    for (;;) {
+        int candidateL = 0;
+        int nextS = 0;
+        bool continue_outer = false;
+        for (;;) {
+            nextS = s + ((s - nextEmit) >> 7) + 1;  // :114
+            if (nextS > sLimit) goto emit_remainder;
+            const int minSrcPos = s - kMaxCopy3Offset + 1;  // :118
+            // lane 0: long(cv)  lane 1: short(cv)  lane 2: repeat  lane 3: long(cv>>8) (used only behind a short hit)
+            uint32_t h = 0;
+            int c = 0;
+            if (lane == 0) h = P::hashL(cv);
+            if (lane == 1) h = P::hashS(cv);
+            if (lane == 3) h = P::hashL(cv >> 8);
+            const uint32_t hL = __shfl_sync(kFullMask, h, 0);
+            if (lane == 0 || lane == 3) c = (int)lTable[h];
+            if (lane == 1) c = (int)sTable[h];
+            if (lane == 3 && h == hL) c = s;  // lTable[hashL] = s precedes the s+1 probe (:124, :207)
+            __syncwarp();
+            if (lane == 0) lTable[h] = (uint32_t)s;
+            if (lane == 1) sTable[h] = (uint32_t)s;
+            uint64_t v = 0;
+            if (lane < 2) v = ldg_u64_unaligned(src + c);                 // valLong / valShort (:127-128)
+            if (lane == 2) v = ldg_u64_unaligned(src + s - repeat);       // :139
+            if (lane == 3) v = ldg_u32_unaligned(src + c);                // :209
+            const uint64_t repeatMask = 0xffffffffull << 8;
+            bool f8 = false, f4 = false;
+            if (lane == 0) {
+                f8 = c > minSrcPos && cv == v;                            // :130
+                f4 = c >= minSrcPos && (uint32_t)cv == (uint32_t)v;       // :199
+            } else if (lane == 1) {
+                f4 = c >= minSrcPos && (uint32_t)cv == (uint32_t)v;       // :204
+            } else if (lane == 2) {
+                f4 = repeat > 0 && (cv & repeatMask) == (v & repeatMask); // :139
+            } else if (lane == 3) {
+                f4 = c > minSrcPos && (uint32_t)(cv >> 8) == (uint32_t)v; // :209
+            }
+            const unsigned m8 = __ballot_sync(kFullMask, f8);
+            const unsigned m4 = __ballot_sync(kFullMask, f4);
+
+            if (m8 & 1u) {  // long candidate matches 8 bytes
+                candidateL = __shfl_sync(kFullMask, c, 0);
+                break;
+            }
+            if (m4 & 4u) {  // repeat at s+1 (:139-196)
+                int base = s + 1;
+                base -= extend_backward(src, base - repeat, base, nextEmit, lane);
+                if (d + (base - nextEmit) > dstLimit) return 0;
+                d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane);
+                const int cand = s - repeat + 4 + 1;
+                s = extend_to_end(src, n, s + 4 + 1, cand, lane);
+                d += emit_repeat(dst + d, s - base, lane);
+                nextEmit = s;
+                if (s >= sLimit) goto emit_remainder;
+                // index in-between (:183-195); program order of one lane keeps "later write wins"
+                int index0 = base + 1;
+                int index1 = s - 2;
+                while (index0 < index1) {
+                    const uint64_t cv0 = ldg_u64_unaligned(src + index0);
+                    const uint64_t cv1 = ldg_u64_unaligned(src + index1);
+                    if (lane == 0) {
+                        lTable[P::hashL(cv0)] = (uint32_t)index0;
+                        sTable[P::hashS(cv0 >> 8)] = (uint32_t)(index0 + 1);
+                        lTable[P::hashL(cv1)] = (uint32_t)index1;
+                        sTable[P::hashS(cv1 >> 8)] = (uint32_t)(index1 + 1);
+                    }
+                    index0 += 2;
+                    index1 -= 2;
+                }
+                __syncwarp();
+                cv = ldg_u64_unaligned(src + s);
+                continue;
+            }
+            if (m4 & 1u) {  // long candidate matches 4 bytes (:199)
+                candidateL = __shfl_sync(kFullMask, c, 0);
+                break;
+            }
+            if (m4 & 2u) {  // short candidate (:204-216): try the long table at s+1
+                if (lane == 3) lTable[h] = (uint32_t)(s + 1);
+                __syncwarp();
+                if (m4 & 8u) {
+                    candidateL = __shfl_sync(kFullMask, c, 3);
+                    s++;
+                } else {
+                    candidateL = __shfl_sync(kFullMask, c, 1);
+                }
+                break;
+            }
+            cv = ldg_u64_unaligned(src + nextS);  // :218
+            s = nextS;
+        }
+
+        {
+            const int back = extend_backward(src, candidateL, s, nextEmit, lane);  // :223-226
+            candidateL -= back;
+            s -= back;
+        }
+        if (d + (s - nextEmit) > dstLimit) return 0;  // :229
+        {
+            const int base = s;
+            const int offset = base - candidateL;
+            s = extend_to_end(src, n, s + 4, candidateL + 4, lane);  // :239-254
+
+            if (offset > 65535 && s - base <= 4 && repeat != offset) {  // :257-264
+                s = nextS + 1;
+                if (s >= sLimit) goto emit_remainder;
+                cv = ldg_u64_unaligned(src + s);
+                continue_outer = true;
+            }
+            if (!continue_outer) {
+                const int nlits = base - nextEmit;  // :266-289
+                if (nlits > 0) {
+                    if (offset <= kMaxCopy2Offset) {
+                        if (nlits > kMaxCopy2Lits || offset < 64) {
+                            d += emit_literal(dst + d, src + nextEmit, nlits, lane);
+                            d += emit_copy(dst + d, offset, s - base, lane);
+                        } else {
+                            d += emit_copy_lits2(dst + d, src + nextEmit, nlits, offset, s - base, lane);
+                        }
+                    } else {
+                        if (nlits > kMaxCopy3Lits) {
+                            d += emit_literal(dst + d, src + nextEmit, nlits, lane);
+                            d += emit_copy(dst + d, offset, s - base, lane);
+                        } else {
+                            d += emit_copy_lits3(dst + d, src + nextEmit, nlits, offset, s - base, lane);
+                        }
+                    }
+                } else {
+                    d += emit_copy(dst + d, offset, s - base, lane);
+                }
+                repeat = offset;
+                nextEmit = s;
+                if (s >= sLimit) goto emit_remainder;  // :293
+                if (d > dstLimit) return 0;            // :297
+
+                // index short & long (:303-326)
+                int index0 = base + 1;
+                int index1 = s - 2;
+                const uint64_t cv0 = ldg_u64_unaligned(src + index0);
+                const uint64_t cv1 = ldg_u64_unaligned(src + index1);
+                if (lane == 0) {
+                    lTable[P::hashL(cv0)] = (uint32_t)index0;
+                    sTable[P::hashS(cv0 >> 8)] = (uint32_t)(index0 + 1);
+                    lTable[P::hashL(cv1)] = (uint32_t)index1;
+                    sTable[P::hashS(cv1 >> 8)] = (uint32_t)(index1 + 1);
+                }
+                index0 += 1;
+                index1 -= 1;
+                cv = ldg_u64_unaligned(src + s);
+                // sparse long-table indexing of the interior; serial order preserved by one lane
+                int index2 = (index0 + index1 + 1) >> 1;
+                while (index2 < index1) {
+                    const uint64_t a = ldg_u64_unaligned(src + index0);
+                    const uint64_t b = ldg_u64_unaligned(src + index2);
+                    if (lane == 0) {
+                        lTable[P::hashL(a)] = (uint32_t)index0;
+                        lTable[P::hashL(b)] = (uint32_t)index2;
+                    }
+                    index0 += 2;
+                    index2 += 2;
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+emit_remainder:  // :329-337
+    if (nextEmit < n) {
+        if (d + n - nextEmit > dstLimit) return 0;
+        d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane);
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(kEncL2Warps * 32)
+encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
+                 const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
+                 uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
+    const int lane = lane_id();
+    const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
+    uint32_t *lTable = tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4);
+    uint32_t *sTable = lTable + (1 << 17);
+    for (;;) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(counter, 1);
+        blk = __shfl_sync(kFullMask, blk, 0);
+        if (blk >= nblk) return;
+        const uint8_t *sp = src + sbeg[blk];
+        const int64_t n64 = (int64_t)(send[blk] - sbeg[blk]);
+        uint8_t *dp = dst + dbeg[blk];
+        int res = 0;
+        if (n64 >= kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {
+            const int n = (int)n64;
+            const bool small = n <= (64 << 10);
+            // zero both tables (the small variant uses the first 2^15 / 2^12 entries)
+            uint4 *t4 = reinterpret_cast<uint4 *>(lTable);
+            const int lwords = small ? (1 << 15) : (1 << 17);
+            const int swords = small ? (1 << 12) : (1 << 14);
+            for (int i = lane; i < lwords / 4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+            uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
+            for (int i = lane; i < swords / 4; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            res = small ? encode_l2_block<true>(dp, sp, n, lTable, sTable, lane)
+                        : encode_l2_block<false>(dp, sp, n, lTable, sTable, lane);
+        }
+        if (lane == 0) out_len[blk] = (uint32_t)res;
+        __syncwarp();
+    }
+}
+
+}  // namespace mz

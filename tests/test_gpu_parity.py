@@ -181,7 +181,7 @@ def test_decode_device_api_no_overrun(oracle):
 
 # ---------------------------------------------------------------- encode ----
 
-@pytest.mark.parametrize("level", [1])
+@pytest.mark.parametrize("level", [1, 2])
 def test_encode_bytes_equal_oracle(oracle, level):
     """Seam level: the CUDA encoder's token stream is byte-identical to the
     oracle's restatement of the Go path, including the 0 = incompressible."""
@@ -198,7 +198,7 @@ def test_encode_bytes_equal_oracle(oracle, level):
     assert not bad, bad[:10]
 
 
-@pytest.mark.parametrize("level", [1])
+@pytest.mark.parametrize("level", [1, 2])
 def test_encode_api_roundtrip(oracle, level):
     """minlz_test.go:138-194 roundtrip through the block API mirror."""
     for name, data in patterns.roundtrip_inputs()[:24] + patterns.reference_patterns()[:12]:
@@ -250,15 +250,12 @@ def test_synthetic_batch_parity(oracle):
     blocks = synth.make_blocks("json", 32, 1 << 20, device="cuda").cpu().numpy()
     src = blocks.reshape(-1)
     soff = (np.arange(33, dtype=np.uint64) << 20)
-    dst, doff, out_len = mz.encode_blocks(src, soff, 1)
-    streams = []
-    for i in range(32):
-        want = oracle.encode_block(blocks[i], 1)
-        got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
-        assert got == want, "block %d" % i
-        streams.append(got)
     for level in (1, 2):
+        dst, doff, out_len = mz.encode_blocks(src, soff, level)
         enc = [oracle.encode_block(blocks[i], level) for i in range(32)]
+        for i in range(32):
+            got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
+            assert got == enc[i], "level %d block %d" % (level, i)
         csrc, csoff = _cat(enc)
         out, status = mz.decode_blocks(csrc, csoff, soff)
         assert not status.any()
