@@ -198,6 +198,7 @@ def main():
     import numpy as np
     import torch
     import minlz_b200 as mz
+    from minlz_b200 import shard
     import synth
 
     if not torch.cuda.is_available():
@@ -224,7 +225,6 @@ def main():
     coff = torch.zeros(nblk + 1, dtype=torch.int64, device=dev)
     dec = torch.empty(nblk * bs, dtype=torch.uint8, device=dev)
     status = torch.zeros(nblk, dtype=torch.int32, device=dev)
-    all_len = torch.zeros(world * nblk, dtype=torch.int32, device=dev) if world > 1 else None
 
     stream = torch.cuda.current_stream()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -239,7 +239,8 @@ def main():
         if world > 1:
             # the one real exchange of the sharded stream: every rank learns all
             # compressed block sizes (stream order = rank order), 4 B per block
-            dist.all_gather_into_tensor(all_len, out_len)
+            all_len = shard.gather_block_lengths(out_len, world * nblk)
+            shard.stream_offsets(all_len, per_block_overhead=8)
         if timed is not None:
             ev[2].record(stream)
         mz.decode_blocks_dev(comp, coff, dec, soff, status)
