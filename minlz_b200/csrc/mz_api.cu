@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "mz_decode.cuh"
+#include "mz_decode_pc.cuh"
 #include "mz_encode_l1.cuh"
 #include "mz_encode_l2.cuh"
 #include "mz_pack.cuh"
@@ -85,6 +86,9 @@ int init_device(int device) {
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.enc_l2_ctas_per_sm, mz::encode_l2_kernel,
                                                               mz::kEncL2Warps * 32, 0);
         if (st.enc_l2_ctas_per_sm < 1) st.enc_l2_ctas_per_sm = 1;
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mz::decode_pc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)mz::kDecSmemBytes);
         st.init_err = e;
     });
     if (st.init_err != cudaSuccess)
@@ -96,11 +100,15 @@ int init_device(int device) {
 // ---- launches --------------------------------------------------------------
 int launch_decode(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint8_t *dst,
                   const uint64_t *dbeg, const uint64_t *dend, int32_t *status, cudaStream_t stream) {
-    (void)device;
     if (nblk == 0) return MZCU_OK;
-    constexpr int kWarps = 4;
-    int grid = (nblk + kWarps - 1) / kWarps;
-    mz::decode_warp_serial_kernel<kWarps><<<grid, kWarps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, dend, status);
+    // up to 32 blocks per CTA (one parser lane each), spread over all SMs
+    const int sms = g_dev[device].num_sms;
+    int slots = (nblk + sms - 1) / sms;
+    if (slots > mz::kDecSlots) slots = mz::kDecSlots;
+    if (slots < 1) slots = 1;
+    const int grid = (nblk + slots - 1) / slots;
+    mz::decode_pc_kernel<<<grid, mz::kDecThreads, mz::kDecSmemBytes, stream>>>(nblk, slots, src, sbeg, send, dst, dbeg,
+                                                                               dend, status);
     CU_TRY(cudaGetLastError());
     return MZCU_OK;
 }
