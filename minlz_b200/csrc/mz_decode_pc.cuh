@@ -46,8 +46,10 @@ constexpr int kDecTok = 32;        // tokens per batch
 constexpr int kDecShort = 64;      // max literal / match length of a "short" token
 constexpr int kDecStage = kDecTok * 2 * kDecShort + 32;       // output image of a batch (+ alignment slack)
 constexpr int kDecLitStage = kDecTok * (8 + kDecShort) + 48;  // stream span of a batch
-constexpr int kDecScratch = 32 * 48;                          // per-lane 32-byte gather landing zone (48 B stride)
+constexpr int kDecScratch = 32 * 48 + 16;                     // per-lane 48-byte gather landing zone
 constexpr int kDescStride = 5 * kDecTok + 1;                  // words per (slot, buffer); odd -> conflict free
+constexpr int kDecRing = 1024;                                // per-slot ring of compressed bytes for the parser
+constexpr int kDecRingAhead = 768;                            // bytes kept loaded ahead of the cursor
 
 struct DecSlotState {  // written by the parser, read by copiers after the barrier
     uint32_t count[2][kDecSlots];   // tokens in the batch | 0x100 if it is a single long token
@@ -56,7 +58,8 @@ struct DecSlotState {  // written by the parser, read by copiers after the barri
 };
 
 constexpr size_t kDecSmemBytes = sizeof(uint32_t) * 2 * kDecSlots * kDescStride + sizeof(DecSlotState) +
-                                 (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch) + 64;
+                                 (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch) +
+                                 (size_t)kDecSlots * kDecRing + 64;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -113,6 +116,76 @@ __device__ __forceinline__ void warp_copy(uint8_t *dstp, const uint8_t *srcp, ui
     if (done + lane < n) dstp[done + lane] = srcp[done + lane];
 }
 
+// Branch-free token parse (layouts: SPEC.md section 2; decode.go:195-308).
+// One lane per block runs this in lockstep with 27+ other lanes, so there is
+// no tag dispatch: every field is computed with selects.
+struct PTok {
+    uint32_t hdr, lit, mlen, off;
+    bool isrep;
+};
+__device__ __forceinline__ PTok parse_token_bf(uint64_t w) {
+    const uint32_t lo = (uint32_t)w;
+    const uint32_t b0 = lo & 0xff;
+    const uint32_t tag = lo & 3;
+    const bool t0 = tag == 0, t1 = tag == 1, t2 = tag == 2;
+    const bool bit2 = (lo & 4) != 0;
+    const bool c3 = tag == 3 && bit2;   // copy3
+    const bool fz = tag == 3 && !bit2;  // fused copy2
+    // length code, and how many extension bytes follow the fixed header
+    const uint32_t code = t0 ? b0 >> 3 : t1 ? (b0 >> 2) & 15 : t2 ? b0 >> 2 : (lo >> 5) & 63;
+    const uint32_t thr = t0 ? 28u : t1 ? 14u : 60u;
+    uint32_t ext = code > thr ? code - thr : 0;
+    if (fz) ext = 0;
+    const uint32_t fixed = t0 ? 1u : t1 ? 2u : c3 ? 4u : 3u;
+    const uint32_t E = (uint32_t)(w >> (8 * fixed)) & (0xffffffu >> (8 * (3 - ext)));
+    const uint32_t addb = t0 ? 30u : t1 ? 18u : 64u;
+    uint32_t len = ext ? E + addb : code + (t0 ? 1u : 4u);
+    if (fz) len = 4 + ((lo >> 5) & 7);
+    const bool islit = t0 && !bit2;
+    PTok t;
+    t.isrep = t0 && bit2;
+    t.hdr = fixed + ext;
+    t.lit = islit ? len : fz ? ((lo >> 3) & 3) + 1 : c3 ? (lo >> 3) & 3 : 0;
+    t.mlen = islit ? 0 : len;
+    t.off = t1 ? ((lo & 0xffff) >> 6) + 1 : c3 ? (lo >> 11) + kMinCopy3Offset : ((lo >> 8) & 0xffff) + kMinCopy2Offset;
+    return t;
+}
+
+// Copies n (0..16) bytes between two shared-memory regions at arbitrary byte
+// alignment with word accesses: 5 aligned loads + funnel shifts on the source,
+// up to 3 head bytes, up to 4 aligned words and up to 3 tail bytes on the
+// destination.  Byte ranges written by different lanes never overlap, and full
+// words are only stored inside a lane's own range, so lanes do not race.
+// `sbase` / `dbase` must be 4-byte aligned; both regions need 4 bytes of slack.
+__device__ __forceinline__ void smem_put16(const uint8_t *sbase, uint32_t soff, uint8_t *dbase, uint32_t doff, uint32_t n) {
+    if (n == 0) soff = doff = 0;  // idle lanes still execute the (unconditional) loads: keep them in bounds
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(sbase) + (soff >> 2);
+    const unsigned sh = (soff & 3) * 8;
+    const uint32_t a0 = sw[0], a1 = sw[1], a2 = sw[2], a3 = sw[3], a4 = sw[4];
+    const uint32_t S0 = __funnelshift_r(a0, a1, sh), S1 = __funnelshift_r(a1, a2, sh), S2 = __funnelshift_r(a2, a3, sh),
+                   S3 = __funnelshift_r(a3, a4, sh);
+    const uint32_t head = min(n, (4u - (doff & 3u)) & 3u);
+    uint8_t *dp = dbase + doff;
+    if (head > 0) dp[0] = (uint8_t)S0;
+    if (head > 1) dp[1] = (uint8_t)(S0 >> 8);
+    if (head > 2) dp[2] = (uint8_t)(S0 >> 16);
+    const unsigned hs = head * 8;
+    const uint32_t D0 = __funnelshift_r(S0, S1, hs), D1 = __funnelshift_r(S1, S2, hs), D2 = __funnelshift_r(S2, S3, hs),
+                   D3 = S3 >> hs;
+    const uint32_t rem = n - head;
+    const uint32_t nw = rem >> 2, tail = rem & 3;
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dp + head);
+    if (nw > 0) dw[0] = D0;
+    if (nw > 1) dw[1] = D1;
+    if (nw > 2) dw[2] = D2;
+    if (nw > 3) dw[3] = D3;
+    const uint32_t Dt = nw == 0 ? D0 : nw == 1 ? D1 : nw == 2 ? D2 : D3;
+    uint8_t *tp = reinterpret_cast<uint8_t *>(dw + nw);
+    if (tail > 0) tp[0] = (uint8_t)Dt;
+    if (tail > 1) tp[1] = (uint8_t)(Dt >> 8);
+    if (tail > 2) tp[2] = (uint8_t)(Dt >> 16);
+}
+
 __global__ void __launch_bounds__(kDecThreads, 1)
 decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
@@ -122,6 +195,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
     DecSlotState *st = reinterpret_cast<DecSlotState *>(desc + 2 * kDecSlots * kDescStride);
     uint8_t *copier_mem = reinterpret_cast<uint8_t *>(st + 1);
     copier_mem += (16 - (reinterpret_cast<uintptr_t>(copier_mem) & 15)) & 15;
+    uint8_t *rings = copier_mem + (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch);  // [kDecSlots][kDecRing]
     __shared__ int produced[2];  // produced[r & 1]: the parser emitted tokens in round r
 
     const int lane = lane_id();
@@ -130,16 +204,28 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
     const int nslots = min(slots_per_cta, nblk - first_blk);
 
     // ---- parser lane state (warp 0) ----
+    // The parser reads its stream through a per-lane shared-memory ring that is
+    // refilled one round ahead with cp.async, so a step never waits on DRAM
+    // (with 28+ lanes in lockstep, some lane would miss the cache on every step).
+    // Ring positions are relative to `p_abase`, the 16-byte aligned address at or
+    // below the stream start: a = lead + s.
     const uint8_t *p_sp = nullptr;
-    int64_t p_slen = 0, p_dlen = 0, p_s = 0, p_d = 0;
+    int p_slen = 0, p_dlen = 0, p_s = 0, p_d = 0;
     uint32_t p_off = 1;
     bool p_done = true, p_bad = false;
+    uintptr_t p_abase = 0;
+    int p_lead = 0;
+    int p_afill = 0, p_aend = 0, p_ready = 0;  // requested up to afill, landed up to ready, stream ends at aend
+    uint8_t *p_ring = rings + (size_t)lane * kDecRing;
     if (warp == 0 && lane < nslots) {
         const int b = first_blk + lane;
         p_sp = src + sbeg[b];
-        p_slen = (int64_t)(send[b] - sbeg[b]);
-        p_dlen = (int64_t)(dend[b] - dbeg[b]);
+        p_slen = (int)(send[b] - sbeg[b]);
+        p_dlen = (int)(dend[b] - dbeg[b]);
         p_done = false;
+        p_abase = reinterpret_cast<uintptr_t>(p_sp) & ~uintptr_t(15);
+        p_lead = (int)(reinterpret_cast<uintptr_t>(p_sp) - p_abase);
+        p_aend = p_lead + p_slen;
     }
     if (threadIdx.x < 2 * kDecSlots) st->count[threadIdx.x / kDecSlots][threadIdx.x % kDecSlots] = 0;
     __syncthreads();
@@ -150,55 +236,75 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
         if (warp == 0) {
             // ================= PARSER =================
             uint32_t *my = desc + (wb * kDecSlots + lane) * kDescStride;
-            uint32_t cnt = 0;
+            // what was requested last round has landed; request the next stretch
+            cp_async_wait_all();
+            if (!p_done) {
+                const int apos = p_lead + p_s;
+                if (p_afill < (apos & ~15)) p_afill = apos & ~15;  // a long literal run skipped ahead
+                p_ready = p_afill;
+                while (p_afill < p_aend && p_afill - apos < kDecRingAhead) {
+                    cp_async16(p_ring + (p_afill & (kDecRing - 1)), reinterpret_cast<const void *>(p_abase + (uintptr_t)p_afill));
+                    p_afill += 16;
+                }
+            }
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(p_ring);
+            int cnt = 0;
             bool cut = false, longtok = false;
             const uint32_t s_first = (uint32_t)p_s;
             for (int k = 0; k < kDecTok; k++) {
                 const bool act = !p_done && !cut;
                 if (!__any_sync(kFullMask, act)) break;
-                if (act) {
-                    if (p_s >= p_slen) {
-                        p_done = true;  // end of stream: decode.go:615 checks d == len(dst)
-                        if (p_d != p_dlen) p_bad = true;
-                    } else {
-                        const Token t = parse_token(ldg_window(p_sp, p_s, p_slen));
-                        const int64_t s1 = p_s + t.hdr;
-                        bool bad = s1 > p_slen;
-                        if (!bad && t.lit) bad = (int64_t)t.lit > p_dlen - p_d || (int64_t)t.lit > p_slen - s1;
-                        uint32_t off = t.repeat ? p_off : t.off;
-                        if (!bad && t.mlen)
-                            bad = (int64_t)off > p_d + t.lit || (int64_t)t.mlen > p_dlen - p_d - t.lit;
-                        if (bad) {
-                            p_bad = true;
-                            p_done = true;
-                        } else {
-                            const bool lng = t.lit > kDecShort || t.mlen > kDecShort;
-                            if (lng && cnt > 0) {
-                                cut = true;  // a long token travels alone: it starts the next batch
-                            } else {
-                                my[0 * kDecTok + cnt] = (uint32_t)s1;   // literal source (stream position)
-                                my[1 * kDecTok + cnt] = (uint32_t)p_d;  // output position
-                                my[2 * kDecTok + cnt] = t.lit;
-                                my[3 * kDecTok + cnt] = t.mlen;
-                                my[4 * kDecTok + cnt] = off;
-                                cnt++;
-                                p_s = s1 + t.lit;
-                                p_d += (int64_t)t.lit + t.mlen;
-                                if (t.mlen) p_off = off;
-                                if (lng) {
-                                    longtok = true;
-                                    cut = true;
-                                }
-                            }
-                        }
-                    }
+                if (!act) continue;
+                if (p_s >= p_slen) {  // end of stream: decode.go:615 checks d == len(dst)
+                    p_done = true;
+                    p_bad = p_bad || p_d != p_dlen;
+                    continue;
                 }
+                // 8 stream bytes at the cursor, from the ring once they have landed
+                uint64_t w8;
+                const int ap = p_lead + p_s;
+                if (ap + 8 <= p_ready || p_aend <= p_ready) {
+                    const uint32_t a4 = (uint32_t)ap >> 2;
+                    const uint32_t w0 = rw[a4 & (kDecRing / 4 - 1)], w1 = rw[(a4 + 1) & (kDecRing / 4 - 1)],
+                                   w2 = rw[(a4 + 2) & (kDecRing / 4 - 1)];
+                    const unsigned sh = ((unsigned)ap & 3u) * 8;
+                    w8 = (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
+                } else {
+                    w8 = ldg_window(p_sp, p_s, p_slen);
+                }
+                const PTok t = parse_token_bf(w8);
+                const int s1 = p_s + (int)t.hdr;
+                const uint32_t off = t.isrep ? p_off : t.off;
+                const int lit = (int)t.lit, mlen = (int)t.mlen;
+                // the reference's checks: header inside src; literals fit src and dst
+                // (decode.go:221,410); offset <= bytes produced, copy fits dst (:326,:572)
+                bool bad = s1 > p_slen || lit > p_dlen - p_d || lit > p_slen - s1;
+                bad = bad || (mlen != 0 && ((int)off > p_d + lit || mlen > p_dlen - p_d - lit));
+                if (bad) {
+                    p_bad = true;
+                    p_done = true;
+                    continue;
+                }
+                const bool lng = lit > kDecShort || mlen > kDecShort;
+                if (lng && cnt > 0) {
+                    cut = true;  // a long token travels alone: it starts the next batch
+                    continue;
+                }
+                my[0 * kDecTok + cnt] = (uint32_t)s1;   // literal source (stream position)
+                my[1 * kDecTok + cnt] = (uint32_t)p_d;  // output position
+                my[2 * kDecTok + cnt] = t.lit;
+                my[3 * kDecTok + cnt] = t.mlen;
+                my[4 * kDecTok + cnt] = off;
+                cnt++;
+                p_s = s1 + lit;
+                p_d += lit + mlen;
+                if (mlen) p_off = off;
+                longtok = lng;
+                cut = lng;
             }
-            if (lane < kDecSlots) {
-                st->count[wb][lane] = cnt | (longtok ? 0x100u : 0u);
-                st->s_first[wb][lane] = s_first;
-                st->s_end[wb][lane] = (uint32_t)p_s;
-            }
+            st->count[wb][lane] = (uint32_t)cnt | (longtok ? 0x100u : 0u);
+            st->s_first[wb][lane] = s_first;
+            st->s_end[wb][lane] = (uint32_t)p_s;
             // an empty batch means every block of this CTA is finished (a lane that is
             // not done always emits at least one token per round)
             const bool some = __any_sync(kFullMask, cnt > 0);
@@ -250,9 +356,10 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 const uint32_t span_chunks = (lshift + (s_end - s_first) + 15) / 16;
                 for (uint32_t c = lane; c < span_chunks; c += 32)
                     cp_async16(lstage + 16 * c, reinterpret_cast<const void *>(a0 + 16 * (uintptr_t)c));
-                // 2. back-reference gathers of tokens whose source is complete (ends before this span)
-                const uint32_t m = dpos + lit;          // output position of the match
-                const uint32_t srcpos = m - off;        // its source
+                // 2. back-reference gathers of tokens whose source is complete (ends before
+                //    this span): up to 32 source bytes = three aligned 16-byte chunks per lane
+                const uint32_t m = dpos + lit;    // output position of the match
+                const uint32_t srcpos = m - off;  // its source
                 const bool has_m = lane < n && mlen > 0;
                 const bool indep = has_m && srcpos + mlen <= x0;
                 const bool dep = has_m && !indep;
@@ -262,42 +369,43 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     const uint8_t *g = dp + srcpos;
                     const uintptr_t ga = reinterpret_cast<uintptr_t>(g) & ~uintptr_t(15);
                     g15 = (uint32_t)(reinterpret_cast<uintptr_t>(g) - ga);
+                    const uint32_t need = g15 + min(mlen, 32u);
                     cp_async16(myscr, reinterpret_cast<const void *>(ga));
-                    if (g15 + min(mlen, 16u) > 16) cp_async16(myscr + 16, reinterpret_cast<const void *>(ga + 16));
+                    if (need > 16) cp_async16(myscr + 16, reinterpret_cast<const void *>(ga + 16));
+                    if (need > 32) cp_async16(myscr + 32, reinterpret_cast<const void *>(ga + 32));
                 }
                 cp_async_wait_all();
                 __syncwarp();
-                // 3. literals: lstage -> stage
+                const uint32_t T = shift + (dpos - x0);  // stage offset of this token's output
+                // 3. literals: lstage -> stage, 16 bytes per pass
                 {
-                    uint32_t maxlit = lit;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) maxlit = max(maxlit, __shfl_xor_sync(kFullMask, maxlit, o));
-                    const uint8_t *ls = lstage + lshift + (litpos - s_first);
-                    uint8_t *ds = stage + shift + (dpos - x0);
-                    for (uint32_t i = 0; i < maxlit; i++)
-                        if (i < lit) ds[i] = ls[i];
+                    const uint32_t loff = lshift + (litpos - s_first);
+                    for (uint32_t done = 0;; done += 16) {
+                        const uint32_t nb = lit > done ? min(lit - done, 16u) : 0;
+                        if (!__any_sync(kFullMask, nb != 0)) break;
+                        smem_put16(lstage, loff + done, stage, T + done, nb);
+                    }
                 }
-                // 4. independent matches: scratch -> stage, 16 bytes per round
+                // 4. independent matches: scratch -> stage; 32 source bytes per gather
                 {
-                    uint8_t *ds = stage + shift + (m - x0);
-                    uint32_t done = 0;
-                    for (;;) {
-                        const uint32_t left = indep && mlen > done ? mlen - done : 0;
-                        const uint32_t take = min(left, 16u);
-                        const uint8_t *ss = myscr + g15;
-#pragma unroll
-                        for (int i = 0; i < 16; i++)
-                            if ((uint32_t)i < take) ds[done + i] = ss[i];
-                        done += 16;
+                    const uint32_t Tm = T + lit;
+                    for (uint32_t done = 0;;) {
+                        const uint32_t n0 = indep && mlen > done ? min(mlen - done, 16u) : 0;
+                        smem_put16(myscr, g15, stage, Tm + done, n0);
+                        const uint32_t n1 = indep && mlen > done + 16 ? min(mlen - done - 16, 16u) : 0;
+                        if (__any_sync(kFullMask, n1 != 0)) smem_put16(myscr, g15 + 16, stage, Tm + done + 16, n1);
+                        done += 32;
                         const bool more = indep && mlen > done;
                         if (!__any_sync(kFullMask, more)) break;
                         __syncwarp();
-                        if (more) {  // next 16 source bytes
+                        if (more) {  // next 32 source bytes
                             const uint8_t *g = dp + srcpos + done;
                             const uintptr_t ga = reinterpret_cast<uintptr_t>(g) & ~uintptr_t(15);
                             g15 = (uint32_t)(reinterpret_cast<uintptr_t>(g) - ga);
+                            const uint32_t need = g15 + min(mlen - done, 32u);
                             cp_async16(myscr, reinterpret_cast<const void *>(ga));
-                            if (g15 + min(mlen - done, 16u) > 16) cp_async16(myscr + 16, reinterpret_cast<const void *>(ga + 16));
+                            if (need > 16) cp_async16(myscr + 16, reinterpret_cast<const void *>(ga + 16));
+                            if (need > 32) cp_async16(myscr + 32, reinterpret_cast<const void *>(ga + 32));
                         }
                         cp_async_wait_all();
                         __syncwarp();
