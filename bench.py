@@ -95,7 +95,7 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def cpu_round_trip(host_blocks, nthreads, repeats=2):
+def cpu_round_trip(host_blocks, nthreads, repeats=2, level=1):
     """Times the oracle port (test/bench infrastructure) on host cores:
     L1 encode + decode of `host_blocks` ([n, bs] uint8 numpy).  Returns GB/s
     of uncompressed bytes over the encode+decode time, and the parts."""
@@ -111,7 +111,7 @@ def cpu_round_trip(host_blocks, nthreads, repeats=2):
     best_e = best_d = 1e30
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out_len = oracle.encode_batch_mt(1, src, soff, enc, doff, nthreads)
+        out_len = oracle.encode_batch_mt(level, src, soff, enc, doff, nthreads)
         t1 = time.perf_counter()
         best_e = min(best_e, t1 - t0)
     assert (out_len > 0).all()
@@ -150,7 +150,7 @@ def run_reference(args):
     t_tot = 0.0
     res = None
     for _ in range(args.steps):
-        res = cpu_round_trip(blocks, cores, repeats=1)
+        res = cpu_round_trip(blocks, cores, repeats=1, level=args.level)
         t_tot += res["seconds"]
     value = nsample * args.block_size * args.steps / t_tot / 1e9
     line = {
@@ -168,9 +168,11 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": "configs[1]+[2]: %d x %d B synthetic %s blocks per GPU, LevelFastest encode (encode_l1) then "
-                        "batched decode of the packed token streams" % (args.blocks, args.block_size, args.kind),
-            "blocks_per_gpu": args.blocks, "block_size": args.block_size, "level": 1,
+    return {"workload": "configs[1]+[2]: %d x %d B synthetic %s blocks per GPU, %s encode then "
+                        "batched decode of the packed token streams" %
+                        (args.blocks, args.block_size, args.kind,
+                         "LevelFastest (encode_l1)" if args.level == 1 else "LevelBalanced (encode_l2)"),
+            "blocks_per_gpu": args.blocks, "block_size": args.block_size, "level": args.level,
             "cache": "inputs (%.1f GB per pass) larger than the 126 MB L2, no flush needed" %
                      (args.blocks * args.block_size / 1e9)}
 
@@ -184,6 +186,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=4096)
     ap.add_argument("--block-size", type=int, default=1 << 20)
     ap.add_argument("--kind", default="json")
+    ap.add_argument("--level", type=int, default=1, help="1 = LevelFastest (headline), 2 = LevelBalanced")
     ap.add_argument("--cpu-blocks", type=int, default=1024, help="bounded sample for the CPU legs")
     ap.add_argument("--e2e-blocks", type=int, default=4096, help="blocks per e2e step (host buffers)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -232,7 +235,7 @@ def main():
     def step(timed):
         if timed is not None:
             ev[0].record(stream)
-        mz.encode_blocks_dev(src, soff, enc, eoff, out_len, mz.LevelFastest)
+        mz.encode_blocks_dev(src, soff, enc, eoff, out_len, args.level)
         if timed is not None:
             ev[1].record(stream)
         mz.pack_blocks_dev(enc, eoff, out_len, comp, coff)
@@ -302,7 +305,7 @@ def main():
 
         def e2e_step():
             # host blocks -> packed token streams on the host -> host blocks again
-            cb_ = mz.encode_blocks_packed_into(n_src, hs, n_comp, hc, mz.LevelFastest, device=local)
+            cb_ = mz.encode_blocks_packed_into(n_src, hs, n_comp, hc, args.level, device=local)
             mz.decode_blocks_into(n_comp, hc, n_dec, hs, hst, device=local)
             return cb_
 
@@ -338,16 +341,16 @@ def main():
     enc_gbs = enc_bytes / (enc_ms / K * 1e-3) / 1e9
     dec_gbs = dec_bytes / (dec_ms / K * 1e-3) / 1e9
     dominant_is_enc = enc_ms >= dec_ms
-    roof = {"bound": "hbm", "kernel": "encode_l1_kernel" if dominant_is_enc else "decode kernel",
+    roof = {"bound": "hbm", "kernel": ("encode_l%d_kernel" % args.level) if dominant_is_enc else "decode_pc_kernel",
             "achieved": round(enc_gbs if dominant_is_enc else dec_gbs, 3), "peak": peak, "unit": "GB/s",
             "frac": round((enc_gbs if dominant_is_enc else dec_gbs) / peak, 5),
             "traffic": ncu_traffic("encode" if dominant_is_enc else "decode"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": enc_bytes if dominant_is_enc else dec_bytes,
             "share_of_step": round((enc_ms if dominant_is_enc else dec_ms) / total_ms, 4)}
-    roof_dec = {"bound": "hbm", "kernel": "decode kernel", "achieved": round(dec_gbs, 3), "peak": peak, "unit": "GB/s",
+    roof_dec = {"bound": "hbm", "kernel": "decode_pc_kernel", "achieved": round(dec_gbs, 3), "peak": peak, "unit": "GB/s",
                 "frac": round(dec_gbs / peak, 5), "traffic": ncu_traffic("decode"),
                 "algorithmic_bytes_per_launch": dec_bytes, "share_of_step": round(dec_ms / total_ms, 4)}
-    roof_enc = {"bound": "hbm", "kernel": "encode_l1_kernel", "achieved": round(enc_gbs, 3), "peak": peak, "unit": "GB/s",
+    roof_enc = {"bound": "hbm", "kernel": "encode_l%d_kernel" % args.level, "achieved": round(enc_gbs, 3), "peak": peak, "unit": "GB/s",
                 "frac": round(enc_gbs / peak, 5), "traffic": ncu_traffic("encode"),
                 "algorithmic_bytes_per_launch": enc_bytes, "share_of_step": round(enc_ms / total_ms, 4)}
 
@@ -356,7 +359,7 @@ def main():
         cores = os.cpu_count() or 1
         nsample = min(nblk, args.cpu_blocks)
         hb = src[: nsample * bs].cpu().numpy().reshape(nsample, bs)
-        r = cpu_round_trip(hb, cores, repeats=2)
+        r = cpu_round_trip(hb, cores, repeats=2, level=args.level)
         cpu = {"value": round(r["value"], 4), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d of the %d blocks, L1 encode + decode, best of 2, oracle port of the Go path "
                          "(the Go/asm reference cannot be built here: no Go toolchain)" % (nsample, nblk),
