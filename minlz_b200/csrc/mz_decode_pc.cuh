@@ -251,56 +251,62 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             int cnt = 0;
             bool cut = false, longtok = false;
             const uint32_t s_first = (uint32_t)p_s;
+            // One token per lane per step, straight-line predicated code.  The loop is
+            // software pipelined: the 8 bytes of the NEXT token are requested from the
+            // ring as soon as this token's header + literal length is known, so the
+            // step-to-step dependency is cursor -> ring load -> length -> cursor and
+            // validation / descriptor stores overlap the load.
+            auto ring_ok_at = [&](int ap) { return ap + 8 <= p_ready || p_aend <= p_ready; };
+            auto ring_load = [&](int ap) {
+                const uint32_t a4 = (uint32_t)ap >> 2;
+                const uint32_t w0 = rw[a4 & (kDecRing / 4 - 1)], w1 = rw[(a4 + 1) & (kDecRing / 4 - 1)],
+                               w2 = rw[(a4 + 2) & (kDecRing / 4 - 1)];
+                const unsigned sh = ((unsigned)ap & 3u) * 8;
+                return (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
+            };
+            uint64_t w8 = ring_load(p_lead + p_s);
+            bool w_ok = ring_ok_at(p_lead + p_s);
             for (int k = 0; k < kDecTok; k++) {
                 const bool act = !p_done && !cut;
                 if (!__any_sync(kFullMask, act)) break;
-                if (!act) continue;
-                if (p_s >= p_slen) {  // end of stream: decode.go:615 checks d == len(dst)
-                    p_done = true;
-                    p_bad = p_bad || p_d != p_dlen;
-                    continue;
-                }
-                // 8 stream bytes at the cursor, from the ring once they have landed
-                uint64_t w8;
-                const int ap = p_lead + p_s;
-                if (ap + 8 <= p_ready || p_aend <= p_ready) {
-                    const uint32_t a4 = (uint32_t)ap >> 2;
-                    const uint32_t w0 = rw[a4 & (kDecRing / 4 - 1)], w1 = rw[(a4 + 1) & (kDecRing / 4 - 1)],
-                                   w2 = rw[(a4 + 2) & (kDecRing / 4 - 1)];
-                    const unsigned sh = ((unsigned)ap & 3u) * 8;
-                    w8 = (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
-                } else {
-                    w8 = ldg_window(p_sp, p_s, p_slen);
+                const bool at_end = p_s >= p_slen;  // decode.go:615 checks d == len(dst) here
+                const bool live = act && !at_end;
+                if (__any_sync(kFullMask, live && !w_ok)) {  // first round / after a long literal run
+                    if (live && !w_ok) w8 = ldg_window(p_sp, p_s, p_slen);
                 }
                 const PTok t = parse_token_bf(w8);
-                const int s1 = p_s + (int)t.hdr;
-                const uint32_t off = t.isrep ? p_off : t.off;
                 const int lit = (int)t.lit, mlen = (int)t.mlen;
+                const int s1 = p_s + (int)t.hdr;
+                const int s_next = s1 + lit;
+                // request the next token's bytes now (speculative: used only if this one is emitted)
+                const uint64_t w8n = ring_load(p_lead + s_next);
+                const bool wn_ok = ring_ok_at(p_lead + s_next);
+                const uint32_t off = t.isrep ? p_off : t.off;
                 // the reference's checks: header inside src; literals fit src and dst
                 // (decode.go:221,410); offset <= bytes produced, copy fits dst (:326,:572)
-                bool bad = s1 > p_slen || lit > p_dlen - p_d || lit > p_slen - s1;
-                bad = bad || (mlen != 0 && ((int)off > p_d + lit || mlen > p_dlen - p_d - lit));
-                if (bad) {
-                    p_bad = true;
-                    p_done = true;
-                    continue;
-                }
+                const int room = p_dlen - p_d - lit;
+                const bool bad = s1 > p_slen || room < 0 || lit > p_slen - s1 ||
+                                 (mlen != 0 && ((int)off > p_d + lit || mlen > room));
                 const bool lng = lit > kDecShort || mlen > kDecShort;
-                if (lng && cnt > 0) {
-                    cut = true;  // a long token travels alone: it starts the next batch
-                    continue;
+                const bool defer = lng && cnt > 0;  // a long token travels alone: it starts the next batch
+                const bool emit = live && !bad && !defer;
+                if (emit) {
+                    my[0 * kDecTok + cnt] = (uint32_t)s1;   // literal source (stream position)
+                    my[1 * kDecTok + cnt] = (uint32_t)p_d;  // output position
+                    my[2 * kDecTok + cnt] = t.lit;
+                    my[3 * kDecTok + cnt] = t.mlen;
+                    my[4 * kDecTok + cnt] = off;
                 }
-                my[0 * kDecTok + cnt] = (uint32_t)s1;   // literal source (stream position)
-                my[1 * kDecTok + cnt] = (uint32_t)p_d;  // output position
-                my[2 * kDecTok + cnt] = t.lit;
-                my[3 * kDecTok + cnt] = t.mlen;
-                my[4 * kDecTok + cnt] = off;
-                cnt++;
-                p_s = s1 + lit;
-                p_d += lit + mlen;
-                if (mlen) p_off = off;
-                longtok = lng;
-                cut = lng;
+                p_bad = p_bad || (act && at_end && p_d != p_dlen) || (live && bad);
+                p_done = p_done || (act && at_end) || (live && bad);
+                cut = cut || (live && !bad && lng);  // deferred, or emitted as the only token of its batch
+                longtok = longtok || (emit && lng);
+                p_off = emit && mlen != 0 ? off : p_off;
+                p_s = emit ? s_next : p_s;
+                p_d = emit ? p_d + lit + mlen : p_d;
+                cnt += emit ? 1 : 0;
+                w8 = emit ? w8n : w8;
+                w_ok = emit ? wn_ok : w_ok;
             }
             st->count[wb][lane] = (uint32_t)cnt | (longtok ? 0x100u : 0u);
             st->s_first[wb][lane] = s_first;
