@@ -17,7 +17,10 @@
 //     every token exactly like the reference, and emits fully resolved
 //     descriptors {literal source, output position, literal length, match
 //     length, offset} into shared memory, 32 tokens per block per round.
-//   * COPIER warps: lane k owns token k of a batch.  All 32 back-reference
+//   * COPIER warps: lane k owns token k of a batch: it decodes the token's
+//     fields, a warp prefix sum gives its output position, a "last defined"
+//     scan resolves repeat offsets, and every token is validated exactly like
+//     the reference (decode.go:221,326,410,572).  Then all 32 back-reference
 //     gathers of a batch go out together (16-byte cp.async per lane into
 //     shared memory), literals come from one coalesced load of the batch's
 //     stream span, everything is assembled in a shared-memory image of the
@@ -47,14 +50,22 @@ constexpr int kDecShort = 64;      // max literal / match length of a "short" to
 constexpr int kDecStage = kDecTok * 2 * kDecShort + 32;       // output image of a batch (+ alignment slack)
 constexpr int kDecLitStage = kDecTok * (8 + kDecShort) + 48;  // stream span of a batch
 constexpr int kDecScratch = 32 * 48 + 16;                     // per-lane 48-byte gather landing zone
-constexpr int kDescStride = 5 * kDecTok + 1;                  // words per (slot, buffer); odd -> conflict free
+constexpr int kDescStride = 3 * kDecTok + 1;                  // words per (slot, buffer); odd -> conflict free
 constexpr int kDecRing = 1024;                                // per-slot ring of compressed bytes for the parser
 constexpr int kDecRingAhead = 768;                            // bytes kept loaded ahead of the cursor
 
-struct DecSlotState {  // written by the parser, read by copiers after the barrier
-    uint32_t count[2][kDecSlots];   // tokens in the batch | 0x100 if it is a single long token
-    uint32_t s_first[2][kDecSlots]; // stream span of the batch: [s_first, s_end)
+constexpr uint32_t kBatchLong = 0x100;   // the batch is a single long token
+constexpr uint32_t kBatchEnded = 0x200;  // the stream ended behind this batch (decode.go:615 check is due)
+constexpr uint32_t kBatchBad = 0x400;    // the parser hit a token that does not fit the stream
+
+struct DecSlotState {
+    // written by the parser, read by the copiers after the barrier
+    uint32_t count[2][kDecSlots];    // tokens in the batch | kBatch* flags
+    uint32_t s_first[2][kDecSlots];  // stream span of the batch: [s_first, s_end)
     uint32_t s_end[2][kDecSlots];
+    // owned by the copier warp of the slot: output cursor, repeat offset, failed
+    uint32_t d[kDecSlots], off[kDecSlots], dead[kDecSlots];
+    uint8_t lut[256];  // first token byte -> header + literal bytes (bit 7: needs the slow path)
 };
 
 constexpr size_t kDecSmemBytes = sizeof(uint32_t) * 2 * kDecSlots * kDescStride + sizeof(DecSlotState) +
@@ -186,17 +197,30 @@ __device__ __forceinline__ void smem_put16(const uint8_t *sbase, uint32_t soff, 
     if (tail > 2) tp[2] = (uint8_t)(Dt >> 16);
 }
 
+__device__ __forceinline__ uint8_t dec_lut_entry(uint32_t b0) {
+    const uint32_t tag = b0 & 3;
+    if (tag == 0) {
+        const uint32_t x = b0 >> 3;
+        if (x >= 29) return 0x80;                                 // extended length
+        return (uint8_t)((b0 & 4) ? 1 : 1 + x + 1);               // repeat: 1 byte; literal: header + x+1 bytes
+    }
+    if (tag == 1) return ((b0 >> 2) & 15) == 15 ? 0x80 : 2;
+    if (tag == 2) return (b0 >> 2) > 60 ? 0x80 : 3;
+    if ((b0 & 4) == 0) return (uint8_t)(3 + ((b0 >> 3) & 3) + 1);  // fused copy2 + 1..4 literals
+    return (uint8_t)(4 + ((b0 >> 3) & 3));                         // copy3 + 0..3 literals (extension checked inline)
+}
+
 __global__ void __launch_bounds__(kDecThreads, 1)
 decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                  const uint64_t *__restrict__ dend, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t *desc = reinterpret_cast<uint32_t *>(smem_raw);  // [2][kDecSlots][kDescStride]
+    uint32_t *desc = reinterpret_cast<uint32_t *>(smem_raw);  // [2][kDecSlots][kDescStride]: pos, header lo, header hi
     DecSlotState *st = reinterpret_cast<DecSlotState *>(desc + 2 * kDecSlots * kDescStride);
     uint8_t *copier_mem = reinterpret_cast<uint8_t *>(st + 1);
     copier_mem += (16 - (reinterpret_cast<uintptr_t>(copier_mem) & 15)) & 15;
     uint8_t *rings = copier_mem + (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch);  // [kDecSlots][kDecRing]
-    __shared__ int produced[2];  // produced[r & 1]: the parser emitted tokens in round r
+    __shared__ int produced[2];  // produced[r & 1]: the parser emitted something in round r
 
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -210,9 +234,8 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
     // Ring positions are relative to `p_abase`, the 16-byte aligned address at or
     // below the stream start: a = lead + s.
     const uint8_t *p_sp = nullptr;
-    int p_slen = 0, p_dlen = 0, p_s = 0, p_d = 0;
-    uint32_t p_off = 1;
-    bool p_done = true, p_bad = false;
+    int p_slen = 0, p_s = 0;
+    bool p_done = true;
     uintptr_t p_abase = 0;
     int p_lead = 0;
     int p_afill = 0, p_aend = 0, p_ready = 0;  // requested up to afill, landed up to ready, stream ends at aend
@@ -221,18 +244,23 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
         const int b = first_blk + lane;
         p_sp = src + sbeg[b];
         p_slen = (int)(send[b] - sbeg[b]);
-        p_dlen = (int)(dend[b] - dbeg[b]);
         p_done = false;
         p_abase = reinterpret_cast<uintptr_t>(p_sp) & ~uintptr_t(15);
         p_lead = (int)(reinterpret_cast<uintptr_t>(p_sp) - p_abase);
         p_aend = p_lead + p_slen;
     }
-    if (threadIdx.x < 2 * kDecSlots) st->count[threadIdx.x / kDecSlots][threadIdx.x % kDecSlots] = 0;
+    if (threadIdx.x < 256) st->lut[threadIdx.x] = dec_lut_entry(threadIdx.x);
+    if (threadIdx.x < kDecSlots) {
+        st->count[0][threadIdx.x] = st->count[1][threadIdx.x] = 0;
+        st->d[threadIdx.x] = 0;
+        st->off[threadIdx.x] = 1;  // decode.go:186
+        st->dead[threadIdx.x] = 0;
+    }
     __syncthreads();
 
     for (int round = 0;; round++) {
-        const int wb = round & 1;        // buffer the parser fills
-        const int rb = wb ^ 1;           // buffer the copiers drain (filled in the previous round)
+        const int wb = round & 1;  // buffer the parser fills
+        const int rb = wb ^ 1;     // buffer the copiers drain (filled in the previous round)
         if (warp == 0) {
             // ================= PARSER =================
             uint32_t *my = desc + (wb * kDecSlots + lane) * kDescStride;
@@ -248,14 +276,6 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 }
             }
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(p_ring);
-            int cnt = 0;
-            bool cut = false, longtok = false;
-            const uint32_t s_first = (uint32_t)p_s;
-            // One token per lane per step, straight-line predicated code.  The loop is
-            // software pipelined: the 8 bytes of the NEXT token are requested from the
-            // ring as soon as this token's header + literal length is known, so the
-            // step-to-step dependency is cursor -> ring load -> length -> cursor and
-            // validation / descriptor stores overlap the load.
             auto ring_ok_at = [&](int ap) { return ap + 8 <= p_ready || p_aend <= p_ready; };
             auto ring_load = [&](int ap) {
                 const uint32_t a4 = (uint32_t)ap >> 2;
@@ -264,56 +284,61 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 const unsigned sh = ((unsigned)ap & 3u) * 8;
                 return (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
             };
+            int cnt = 0;
+            uint32_t flags = 0;
+            bool cut = false;
+            const uint32_t s_first = (uint32_t)p_s;
             uint64_t w8 = ring_load(p_lead + p_s);
             bool w_ok = ring_ok_at(p_lead + p_s);
             for (int k = 0; k < kDecTok; k++) {
                 const bool act = !p_done && !cut;
                 if (!__any_sync(kFullMask, act)) break;
-                const bool at_end = p_s >= p_slen;  // decode.go:615 checks d == len(dst) here
+                const bool at_end = p_s >= p_slen;
                 const bool live = act && !at_end;
                 if (__any_sync(kFullMask, live && !w_ok)) {  // first round / after a long literal run
                     if (live && !w_ok) w8 = ldg_window(p_sp, p_s, p_slen);
                 }
-                const PTok t = parse_token_bf(w8);
-                const int lit = (int)t.lit, mlen = (int)t.mlen;
-                const int s1 = p_s + (int)t.hdr;
-                const int s_next = s1 + lit;
-                // request the next token's bytes now (speculative: used only if this one is emitted)
-                const uint64_t w8n = ring_load(p_lead + s_next);
-                const bool wn_ok = ring_ok_at(p_lead + s_next);
-                const uint32_t off = t.isrep ? p_off : t.off;
-                // the reference's checks: header inside src; literals fit src and dst
-                // (decode.go:221,410); offset <= bytes produced, copy fits dst (:326,:572)
-                const int room = p_dlen - p_d - lit;
-                const bool bad = s1 > p_slen || room < 0 || lit > p_slen - s1 ||
-                                 (mlen != 0 && ((int)off > p_d + lit || mlen > room));
-                const bool lng = lit > kDecShort || mlen > kDecShort;
+                const uint32_t lo = (uint32_t)w8;
+                const uint32_t e = st->lut[lo & 0xff];
+                const bool c3x = (lo & 7) == 7 && ((lo >> 5) & 63) > 60;  // copy3 with extended length
+                const bool slow = (e & 0x80) != 0 || c3x;
+                int adv = (int)(e & 0x7f);
+                bool lng = false;
+                if (__any_sync(kFullMask, live && slow)) {
+                    if (live && slow) {
+                        const PTok t = parse_token_bf(w8);
+                        adv = (int)(t.hdr + t.lit);
+                        lng = t.lit > kDecShort || t.mlen > kDecShort;
+                    }
+                }
+                // header and literals must lie inside the stream (decode.go:221,410 src side)
+                const bool bad = adv > p_slen - p_s;
                 const bool defer = lng && cnt > 0;  // a long token travels alone: it starts the next batch
                 const bool emit = live && !bad && !defer;
+                const int s_next = p_s + adv;
+                const uint64_t w8n = ring_load(p_lead + s_next);  // speculative: used only if emitted
+                const bool wn_ok = ring_ok_at(p_lead + s_next);
                 if (emit) {
-                    my[0 * kDecTok + cnt] = (uint32_t)s1;   // literal source (stream position)
-                    my[1 * kDecTok + cnt] = (uint32_t)p_d;  // output position
-                    my[2 * kDecTok + cnt] = t.lit;
-                    my[3 * kDecTok + cnt] = t.mlen;
-                    my[4 * kDecTok + cnt] = off;
+                    my[0 * kDecTok + cnt] = (uint32_t)p_s;
+                    my[1 * kDecTok + cnt] = lo;
+                    my[2 * kDecTok + cnt] = (uint32_t)(w8 >> 32);
                 }
-                p_bad = p_bad || (act && at_end && p_d != p_dlen) || (live && bad);
+                flags |= (act && at_end) ? kBatchEnded : 0u;
+                flags |= (live && bad) ? kBatchBad : 0u;
+                flags |= (emit && lng) ? kBatchLong : 0u;
                 p_done = p_done || (act && at_end) || (live && bad);
-                cut = cut || (live && !bad && lng);  // deferred, or emitted as the only token of its batch
-                longtok = longtok || (emit && lng);
-                p_off = emit && mlen != 0 ? off : p_off;
+                cut = cut || (live && !bad && lng);
                 p_s = emit ? s_next : p_s;
-                p_d = emit ? p_d + lit + mlen : p_d;
                 cnt += emit ? 1 : 0;
                 w8 = emit ? w8n : w8;
                 w_ok = emit ? wn_ok : w_ok;
             }
-            st->count[wb][lane] = (uint32_t)cnt | (longtok ? 0x100u : 0u);
+            st->count[wb][lane] = (uint32_t)cnt | flags;
             st->s_first[wb][lane] = s_first;
             st->s_end[wb][lane] = (uint32_t)p_s;
-            // an empty batch means every block of this CTA is finished (a lane that is
-            // not done always emits at least one token per round)
-            const bool some = __any_sync(kFullMask, cnt > 0);
+            // a round that emits nothing (no tokens, no end / error notices) means
+            // every block of this CTA is finished
+            const bool some = __any_sync(kFullMask, cnt > 0 || flags != 0);
             if (lane == 0) produced[wb] = some ? 1 : 0;
         } else if (round > 0) {
             // ================= COPIERS =================
@@ -323,36 +348,90 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             uint8_t *scratch = lstage + kDecLitStage;
             for (int slot = cw; slot < nslots; slot += kDecCopiers) {
                 const uint32_t cword = st->count[rb][slot];
-                const int n = (int)(cword & 0xff);
-                if (n == 0) continue;
+                if (cword == 0 || st->dead[slot]) continue;
+                int n = (int)(cword & 0xff);
                 const int b = first_blk + slot;
                 const uint8_t *sp = src + sbeg[b];
                 uint8_t *dp = dst + dbeg[b];
+                const uint32_t dlen = (uint32_t)(dend[b] - dbeg[b]);
+                const uint32_t d_base = st->d[slot];
+                const uint32_t off_carry = st->off[slot];
+                // ---- decode my token ----
                 const uint32_t *dsc = desc + (rb * kDecSlots + slot) * kDescStride;
-                uint32_t litpos = 0, dpos = 0, lit = 0, mlen = 0, off = 1;
+                uint32_t tp = 0, lit = 0, mlen = 0, off_tok = 0, hdr = 0;
+                bool isrep = false;
                 if (lane < n) {
-                    litpos = dsc[0 * kDecTok + lane];
-                    dpos = dsc[1 * kDecTok + lane];
-                    lit = dsc[2 * kDecTok + lane];
-                    mlen = dsc[3 * kDecTok + lane];
-                    off = dsc[4 * kDecTok + lane];
+                    tp = dsc[lane];
+                    const PTok t = parse_token_bf((uint64_t)dsc[2 * kDecTok + lane] << 32 | dsc[kDecTok + lane]);
+                    lit = t.lit;
+                    mlen = t.mlen;
+                    off_tok = t.off;
+                    hdr = t.hdr;
+                    isrep = t.isrep;
                 }
-                if (cword & 0x100u) {
+                const uint32_t litpos = tp + hdr;
+                // output positions: exclusive prefix sum of lit + mlen
+                const uint32_t olen = lit + mlen;
+                uint32_t incl = olen;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(kFullMask, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                const uint32_t dpos = d_base + incl - olen;
+                // repeat offsets: the last offset defined before me (decode.go:186,214)
+                uint32_t lastdef = (mlen != 0 && !isrep) ? off_tok : 0;  // 0 = none (offsets are >= 1)
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(kFullMask, lastdef, o);
+                    if (lane >= o && lastdef == 0) lastdef = u;
+                }
+                uint32_t prevdef = __shfl_up_sync(kFullMask, lastdef, 1);
+                if (lane == 0 || prevdef == 0) prevdef = lane == 0 ? off_carry : prevdef;
+                if (prevdef == 0) prevdef = off_carry;
+                const uint32_t off = isrep ? prevdef : off_tok;
+                // the reference's dst-side checks (decode.go:221,326,410,572), in stream order
+                bool tbad = false;
+                if (lane < n) {
+                    tbad = dpos > dlen || lit > dlen - dpos;
+                    if (!tbad && mlen != 0) tbad = off > dpos + lit || mlen > dlen - dpos - lit;
+                }
+                const unsigned badm = __ballot_sync(kFullMask, tbad);
+                bool kill = (cword & kBatchBad) != 0;
+                if (badm) {  // keep the tokens before the first bad one, then give up on the block
+                    n = __ffs(badm) - 1;
+                    kill = true;
+                    if (lane >= n) lit = mlen = 0;
+                }
+                const uint32_t total = n > 0 ? __shfl_sync(kFullMask, incl, n - 1) : 0;
+                {
+                    // carry the cursor and the repeat offset to the next batch of this block
+                    const unsigned defm = __ballot_sync(kFullMask, lane < n && mlen != 0 && !isrep);
+                    const uint32_t newoff = defm ? __shfl_sync(kFullMask, off_tok, 31 - __clz(defm)) : off_carry;
+                    if (lane == 0) {
+                        st->d[slot] = d_base + total;
+                        st->off[slot] = newoff;
+                        if ((cword & kBatchEnded) && d_base + total != dlen) kill = true;  // decode.go:615
+                        if (kill) st->dead[slot] = 1;
+                    }
+                }
+                if (n == 0) continue;
+                if (cword & kBatchLong) {
                     // ---- one long token: cooperative copies straight to global memory ----
-                    litpos = __shfl_sync(kFullMask, litpos, 0);
-                    dpos = __shfl_sync(kFullMask, dpos, 0);
-                    lit = __shfl_sync(kFullMask, lit, 0);
-                    mlen = __shfl_sync(kFullMask, mlen, 0);
-                    off = __shfl_sync(kFullMask, off, 0);
-                    if (lit) warp_copy(dp + dpos, sp + litpos, lit, lane);
+                    const uint32_t l_litpos = __shfl_sync(kFullMask, litpos, 0);
+                    const uint32_t l_dpos = __shfl_sync(kFullMask, dpos, 0);
+                    const uint32_t l_lit = __shfl_sync(kFullMask, lit, 0);
+                    const uint32_t l_mlen = __shfl_sync(kFullMask, mlen, 0);
+                    const uint32_t l_off = __shfl_sync(kFullMask, off, 0);
+                    if (l_lit) warp_copy(dp + l_dpos, sp + l_litpos, l_lit, lane);
                     __syncwarp();
-                    if (mlen) warp_copy_overlap(dp + dpos + lit, off, mlen, lane);
+                    if (l_mlen) warp_copy_overlap(dp + l_dpos + l_lit, l_off, l_mlen, lane);
                     __syncwarp();
                     continue;
                 }
                 // ---- batch of short tokens ----
-                const uint32_t x0 = __shfl_sync(kFullMask, dpos, 0);
-                const uint32_t xend = __shfl_sync(kFullMask, dpos + lit + mlen, n - 1);
+                const uint32_t x0 = d_base;
+                const uint32_t xend = d_base + total;
                 const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dp + x0) & 15);  // stage mirrors dst alignment
                 // 1. stream span -> lstage (aligned 16-byte chunks of the absolute address)
                 const uint32_t s_first = st->s_first[rb][slot], s_end = st->s_end[rb][slot];
@@ -453,13 +532,13 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             }
         }
         __syncthreads();
-        // Batch `round` is empty: nothing left to parse, and the copiers drained
-        // batch round-1 in this very round.  (produced[] is double buffered, so the
-        // parser's next write cannot race with this read.)
+        // Round `round` emitted nothing: nothing is left to parse, and the copiers
+        // drained round-1 in this very round.  (produced[] is double buffered, so
+        // the parser's next write cannot race with this read.)
         if (produced[wb] == 0) break;
     }
 
-    if (warp == 0 && lane < nslots) status[first_blk + lane] = p_bad ? 1 : 0;
+    if (threadIdx.x < nslots) status[first_blk + threadIdx.x] = st->dead[threadIdx.x] ? 1 : 0;
 }
 
 }  // namespace mz
