@@ -441,6 +441,11 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 const uint32_t span_chunks = (lshift + (s_end - s_first) + 15) / 16;
                 for (uint32_t c = lane; c < span_chunks; c += 32)
                     cp_async16(lstage + 16 * c, reinterpret_cast<const void *>(a0 + 16 * (uintptr_t)c));
+                // The image is flushed in whole 16-byte chunks.  Its first chunk also holds
+                // the last `shift` bytes of the previous batch: fetch them back (not at the
+                // very start of a block, where those bytes belong to a neighbour).
+                const bool head_ok = x0 > 0;
+                if (lane == 0 && shift != 0 && head_ok) cp_async16(stage, dp + x0 - shift);
                 // 2. back-reference gathers of tokens whose source is complete (ends before
                 //    this span): up to 32 source bytes = three aligned 16-byte chunks per lane
                 const uint32_t m = dpos + lit;    // output position of the match
@@ -521,7 +526,10 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     const uint32_t nchunk = (total + 15) / 16;
                     for (uint32_t c = lane; c < nchunk; c += 32) {
                         const uint32_t lo = 16 * c, hi = lo + 16;
-                        if (lo >= shift && hi <= total) {
+                        // bytes past `total` in the last chunk are this block's future output
+                        // (rewritten by the next batch), so a whole-chunk store is fine unless
+                        // it would cross the end of the block
+                        if ((lo >= shift || head_ok) && (hi <= total || x0 - shift + hi <= dlen)) {
                             *reinterpret_cast<uint4 *>(gbase + lo) = *reinterpret_cast<const uint4 *>(stage + lo);
                         } else {
                             for (uint32_t i = max(lo, shift); i < min(hi, total); i++) gbase[i] = stage[i];
