@@ -121,6 +121,24 @@ int mzcu_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t 
 int mzcu_encode_blocks_packed(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
                               uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out);
 
+/* ---- stream-layer helpers ------------------------------
+ * The stream format frames every block as a chunk that carries the masked
+ * CRC-32C of the UNCOMPRESSED block (minlz.go:133-140 crc; writer.go:672,
+ * reader.go:341-351; SPEC.md stream section 3).  The blocks are resident on
+ * the device for the codec kernels anyway, so the checksum is computed there.
+ *
+ * mzcu_crc32c_blocks[_dev]: crc[i] = masked CRC-32C of block i.
+ * mzcu_stream_encode_blocks: mzcu_encode_blocks_packed + crc_out[i] of the
+ *   source block (what Writer.write needs per block, writer.go:670-696).
+ * mzcu_stream_decode_blocks: mzcu_decode_blocks + crc_out[i] of the decoded
+ *   block (what Reader.Read checks, reader.go:334-351).  crc_out may be NULL. */
+int mzcu_crc32c_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint32_t *crc, void *stream);
+int mzcu_crc32c_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint32_t *crc);
+int mzcu_stream_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                              size_t dst_cap, uint64_t *dst_off_out, uint32_t *crc_out);
+int mzcu_stream_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                              const uint64_t *dst_off, int32_t *status, uint32_t *crc_out);
+
 /* ---- block API level (full blocks with header), host pointers ----------
  *
  * replaces: Encode (encode.go:74-139).  Writes 0x00 + uvarint(len) + tokens,

@@ -20,6 +20,10 @@ SYMBOLS = {
     "mzcu_encode_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "mzcu_encode_blocks_packed": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "mzcu_decode_blocks": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "mzcu_crc32c_blocks_dev": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P]),
+    "mzcu_crc32c_blocks": (C.c_int, [C.c_int, C.c_int, _P, _P, _P]),
+    "mzcu_stream_encode_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P, _P]),
+    "mzcu_stream_decode_blocks": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "mzcu_encode": (C.c_int64, [_P, C.c_size_t, _P, C.c_size_t, C.c_int]),
     "mzcu_try_encode": (C.c_int64, [_P, C.c_size_t, _P, C.c_size_t, C.c_int]),
     "mzcu_decode": (C.c_int64, [_P, C.c_size_t, _P, C.c_size_t]),

@@ -20,6 +20,7 @@
 #include "mz_encode_l1.cuh"
 #include "mz_encode_l2.cuh"
 #include "mz_pack.cuh"
+#include "mz_crc32c.cuh"
 
 namespace {
 
@@ -59,6 +60,7 @@ struct DeviceState {
     int enc_l1_ctas_per_sm = 1;
     int enc_l2_ctas_per_sm = 1;
     int *counters = nullptr;  // kCounterSlots ints
+    mz::CrcTables *crc_tabs = nullptr;
     std::atomic<unsigned> next_counter{0};
     std::mutex ws_mu;
     std::vector<TableWs> table_ws;
@@ -72,12 +74,41 @@ int resolve_device(int device) {
     return (device >= 0 && device < kMaxDevices) ? device : -1;
 }
 
+// CRC-32C (Castagnoli, reflected) byte table and the "advance by 2^k zero
+// bytes" matrices used to combine per-lane partial checksums.
+void build_crc_tables(mz::CrcTables *t) {
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x82f63b78u : c >> 1;
+        t->byte_table[i] = c;
+    }
+    // one zero byte: c -> table[c & 0xff] ^ (c >> 8), applied to each unit vector
+    for (int i = 0; i < 32; i++) {
+        uint32_t c = 1u << i;
+        t->zeros[0][i] = t->byte_table[c & 0xff] ^ (c >> 8);
+    }
+    for (int k = 1; k < 24; k++)  // square the operator
+        for (int i = 0; i < 32; i++) {
+            uint32_t v = t->zeros[k - 1][i], r = 0;
+            for (int b = 0; b < 32; b++)
+                if ((v >> b) & 1) r ^= t->zeros[k - 1][b];
+            t->zeros[k][i] = r;
+        }
+}
+
 int init_device(int device) {
     DeviceState &st = g_dev[device];
     std::call_once(st.once, [&] {
         cudaError_t e = cudaSetDevice(device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, device);
         if (e == cudaSuccess) e = cudaMalloc(&st.counters, kCounterSlots * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&st.crc_tabs, sizeof(mz::CrcTables));
+        if (e == cudaSuccess) {
+            mz::CrcTables *h = new mz::CrcTables();
+            build_crc_tables(h);
+            e = cudaMemcpy(st.crc_tabs, h, sizeof(mz::CrcTables), cudaMemcpyHostToDevice);
+            delete h;
+        }
         if (e == cudaSuccess)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.enc_l1_ctas_per_sm, mz::encode_l1_kernel,
                                                               mz::kEncL1Warps * 32, 0);
@@ -175,6 +206,15 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
     } else {
         return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
     }
+    CU_TRY(cudaGetLastError());
+    return MZCU_OK;
+}
+
+int launch_crc(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint32_t *crc,
+               cudaStream_t stream) {
+    if (nblk == 0) return MZCU_OK;
+    const int grid = (nblk + mz::kCrcWarps - 1) / mz::kCrcWarps;
+    mz::crc32c_blocks_kernel<<<grid, mz::kCrcWarps * 32, 0, stream>>>(nblk, src, sbeg, send, crc, g_dev[device].crc_tabs);
     CU_TRY(cudaGetLastError());
     return MZCU_OK;
 }
@@ -422,7 +462,7 @@ int host_encode_blocks(int device, int level, int nblk, const uint8_t *src, cons
 // Seam-level encode for host buffers with dense output: the token streams are
 // packed back to back on the device and leave with one D2H copy.
 int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
-                              size_t dst_cap, uint64_t *dst_off_out) {
+                              size_t dst_cap, uint64_t *dst_off_out, uint32_t *crc_out) {
     if (nblk < 0 || !dst_off_out || (nblk > 0 && (!src_off || !dst))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
     if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
         return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
@@ -461,6 +501,11 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
     if (total) CU_TRY(cudaMemcpyAsync(w->d_src, src + base, total, cudaMemcpyHostToDevice, w->stream));
     CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 3 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
     CU_TRY(cudaEventRecord(w->ev0, w->stream));
+    uint32_t *d_crc = d_out + T;  // second half of the 5th table row
+    if (crc_out) {  // checksum of the uncompressed blocks while they are resident (writer.go:672)
+        rc = launch_crc(device, nblk, w->d_src, d_sbeg, d_send, d_crc, w->stream);
+        if (rc) return rc;
+    }
     rc = launch_encode(device, level, nblk, w->d_src, d_sbeg, d_send, w->d_dst, d_dbeg, d_out, w->stream);
     if (rc) return rc;
     // the source is dead after the encode: pack into its buffer (sum(len) < total)
@@ -468,6 +513,7 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
     if (rc) return rc;
     CU_TRY(cudaEventRecord(w->ev1, w->stream));
     CU_TRY(cudaMemcpyAsync(h_poff, d_poff, (size_t)(nblk + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, w->stream));
+    if (crc_out) CU_TRY(cudaMemcpyAsync(crc_out, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     CU_TRY(cudaStreamSynchronize(w->stream));
     const size_t packed = h_poff[nblk];
     if (packed > dst_cap) return fail(MZCU_ERR_DST_TOO_SMALL, "packed output %zu > capacity %zu", packed, dst_cap);
@@ -480,7 +526,7 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
 
 // Seam-level decode for host buffers.  `sbeg/send` index into `src`.
 int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint8_t *dst,
-                       const uint64_t *dbeg, const uint64_t *dend, int32_t *status) {
+                       const uint64_t *dbeg, const uint64_t *dend, int32_t *status, uint32_t *crc_out = nullptr) {
     if (nblk == 0) return MZCU_OK;
     device = resolve_device(device);
     if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
@@ -525,6 +571,12 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
     rc = launch_decode(device, nblk, w->d_src, w->d_tab, w->d_tab + T, w->d_dst, w->d_tab + 2 * T, w->d_tab + 3 * T, d_status,
                        w->stream);
     if (rc) return rc;
+    if (crc_out) {  // checksum of the decoded blocks while they are resident (reader.go:341-351)
+        uint32_t *d_crc = reinterpret_cast<uint32_t *>(d_status) + T;
+        rc = launch_crc(device, nblk, w->d_dst, w->d_tab + 2 * T, w->d_tab + 3 * T, d_crc, w->stream);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(crc_out, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    }
     CU_TRY(cudaEventRecord(w->ev1, w->stream));
     CU_TRY(cudaMemcpyAsync(h_status, d_status, (size_t)nblk * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream));
     if (dense) {
@@ -626,7 +678,53 @@ int mzcu_encode_blocks(int device, int level, int nblk, const uint8_t *src, cons
 
 int mzcu_encode_blocks_packed(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
                               uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out) {
-    return host_encode_blocks_packed(device, level, nblk, src, src_off, dst, dst_cap, dst_off_out);
+    return host_encode_blocks_packed(device, level, nblk, src, src_off, dst, dst_cap, dst_off_out, nullptr);
+}
+
+int mzcu_stream_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                              size_t dst_cap, uint64_t *dst_off_out, uint32_t *crc_out) {
+    return host_encode_blocks_packed(device, level, nblk, src, src_off, dst, dst_cap, dst_off_out, crc_out);
+}
+
+int mzcu_stream_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                              const uint64_t *dst_off, int32_t *status, uint32_t *crc_out) {
+    if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !status))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    return host_decode_ranges(device, nblk, src, src_off, src_off + 1, dst, dst_off, dst_off + 1, status, crc_out);
+}
+
+int mzcu_crc32c_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint32_t *crc, void *stream) {
+    if (nblk < 0 || (nblk > 0 && (!src || !src_off || !crc))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    return launch_crc(device, nblk, src, src_off, src_off + 1, crc, (cudaStream_t)stream);
+}
+
+int mzcu_crc32c_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint32_t *crc) {
+    if (nblk < 0 || (nblk > 0 && (!src_off || !crc))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    if (nblk == 0) return MZCU_OK;
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    WsGuard g;
+    rc = ws_acquire(device, &g.w);
+    if (rc) return rc;
+    Workspace *w = g.w;
+    const size_t base = src_off[0], total = src_off[nblk] - base;
+    rc = ws_reserve(w, total, 16, (size_t)nblk);
+    if (rc) return rc;
+    const size_t T = w->cap_tab;
+    for (int i = 0; i <= nblk; i++) w->h_tab[i] = src_off[i] - base;
+    uint32_t *d_crc = reinterpret_cast<uint32_t *>(w->d_tab + 4 * T);
+    if (total) CU_TRY(cudaMemcpyAsync(w->d_src, src + base, total, cudaMemcpyHostToDevice, w->stream));
+    CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, (size_t)(nblk + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+    rc = launch_crc(device, nblk, w->d_src, w->d_tab, w->d_tab + 1, d_crc, w->stream);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(crc, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    return MZCU_OK;
 }
 
 int mzcu_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
