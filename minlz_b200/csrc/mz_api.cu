@@ -130,11 +130,15 @@ int init_device(int device) {
 
 // ---- launches --------------------------------------------------------------
 int launch_decode(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint8_t *dst,
-                  const uint64_t *dbeg, const uint64_t *dend, int32_t *status, cudaStream_t stream) {
+                  const uint64_t *dbeg, const uint64_t *dend, int32_t *status, cudaStream_t stream, int batch_blocks = 0) {
     if (nblk == 0) return MZCU_OK;
-    // up to 32 blocks per CTA (one parser lane each), spread over all SMs
+    // up to 32 blocks per CTA (one parser lane each), spread over all SMs.  When this
+    // launch is one chunk of a larger batch whose chunks run concurrently, size the
+    // CTAs for the whole batch so that the chunks share the SMs instead of each
+    // spreading thinly over all of them.
     const int sms = g_dev[device].num_sms;
-    int slots = (nblk + sms - 1) / sms;
+    const int whole = batch_blocks > nblk ? batch_blocks : nblk;
+    int slots = (whole + sms - 1) / sms;
     if (slots > mz::kDecSlots) slots = mz::kDecSlots;
     if (slots < 1) slots = 1;
     const int grid = (nblk + slots - 1) / slots;
@@ -231,6 +235,9 @@ int launch_pack(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, 
     return MZCU_OK;
 }
 
+constexpr int kMaxChunks = 4;
+constexpr int kMinChunkBlocks = 256;  // do not split batches below this many blocks per chunk
+
 // ---- pooled host-call workspaces ------------------------------------------
 struct Workspace {
     int device = -1;
@@ -241,6 +248,8 @@ struct Workspace {
     uint64_t *d_tab = nullptr;  // 4 offset arrays + out/status
     size_t cap_tab = 0;         // in blocks
     uint64_t *h_tab = nullptr;  // pinned mirror of d_tab
+    cudaStream_t cs[kMaxChunks] = {};  // chunk pipelines (copy in / kernels / copy out overlap across chunks)
+    cudaEvent_t tab_ready = nullptr;
 };
 
 std::mutex g_ws_mu;
@@ -262,6 +271,8 @@ int ws_acquire(int device, Workspace **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
+    for (int c = 0; c < kMaxChunks && e == cudaSuccess; c++) e = cudaStreamCreateWithFlags(&w->cs[c], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->tab_ready, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete w;
         return fail(MZCU_ERR_CUDA, "workspace: %s", cudaGetErrorString(e));
@@ -491,6 +502,7 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
     uint64_t *h_sbeg = w->h_tab, *h_send = w->h_tab + T, *h_dbeg = w->h_tab + 2 * T, *h_poff = w->h_tab + 3 * T;
     uint64_t *d_sbeg = w->d_tab, *d_send = w->d_tab + T, *d_dbeg = w->d_tab + 2 * T, *d_poff = w->d_tab + 3 * T;
     uint32_t *d_out = reinterpret_cast<uint32_t *>(w->d_tab + 4 * T);
+    uint32_t *d_crc = d_out + T;  // second half of the 5th table row
     size_t dof = 0;
     for (int i = 0; i < nblk; i++) {
         h_sbeg[i] = src_off[i] - base;
@@ -498,27 +510,57 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
         h_dbeg[i] = dof;
         dof += (src_off[i + 1] - src_off[i] + 2 + 15) & ~size_t(15);
     }
-    if (total) CU_TRY(cudaMemcpyAsync(w->d_src, src + base, total, cudaMemcpyHostToDevice, w->stream));
+    // Chunk pipeline: the batch is cut into up to kMaxChunks runs of blocks, each on its
+    // own stream (H2D -> crc -> encode -> pack -> D2H of the sizes).  The kernels are
+    // latency bound per block, so chunks overlap on the device while later chunks are
+    // still arriving over PCIe, and packed chunks leave while others still encode.
+    int nchunks = nblk / kMinChunkBlocks;
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    if (nchunks < 1) nchunks = 1;
+    int first[kMaxChunks + 1];
+    for (int c = 0; c <= nchunks; c++) first[c] = (int)((int64_t)nblk * c / nchunks);
     CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 3 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+    CU_TRY(cudaEventRecord(w->tab_ready, w->stream));
     CU_TRY(cudaEventRecord(w->ev0, w->stream));
-    uint32_t *d_crc = d_out + T;  // second half of the 5th table row
-    if (crc_out) {  // checksum of the uncompressed blocks while they are resident (writer.go:672)
-        rc = launch_crc(device, nblk, w->d_src, d_sbeg, d_send, d_crc, w->stream);
+    for (int c = 0; c < nchunks; c++) {
+        cudaStream_t cs = w->cs[c];
+        const int f = first[c], m = first[c + 1] - first[c];
+        const size_t cb = h_sbeg[f], ce = h_send[first[c + 1] - 1];
+        CU_TRY(cudaStreamWaitEvent(cs, w->tab_ready, 0));
+        if (ce > cb) CU_TRY(cudaMemcpyAsync(w->d_src + cb, src + base + cb, ce - cb, cudaMemcpyHostToDevice, cs));
+        if (crc_out) {  // checksum of the uncompressed blocks while they are resident (writer.go:672)
+            rc = launch_crc(device, m, w->d_src, d_sbeg + f, d_send + f, d_crc + f, cs);
+            if (rc) return rc;
+        }
+        rc = launch_encode(device, level, m, w->d_src, d_sbeg + f, d_send + f, w->d_dst, d_dbeg + f, d_out + f, cs);
         if (rc) return rc;
+        // the chunk's source is dead after its encode: pack into its own source range
+        // (sum(len) < chunk bytes); the chunk's offsets start at 0 (own poff slice, stride m+1)
+        rc = launch_pack(device, m, w->d_dst, d_dbeg + f, d_out + f, w->d_src + cb, d_poff + f + c, cs);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(h_poff + f + c, d_poff + f + c, (size_t)(m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, cs));
+        if (crc_out) CU_TRY(cudaMemcpyAsync(crc_out + f, d_crc + f, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
     }
-    rc = launch_encode(device, level, nblk, w->d_src, d_sbeg, d_send, w->d_dst, d_dbeg, d_out, w->stream);
-    if (rc) return rc;
-    // the source is dead after the encode: pack into its buffer (sum(len) < total)
-    rc = launch_pack(device, nblk, w->d_dst, d_dbeg, d_out, w->d_src, d_poff, w->stream);
-    if (rc) return rc;
+    size_t host_pos = 0;
+    for (int c = 0; c < nchunks; c++) {
+        cudaStream_t cs = w->cs[c];
+        const int f = first[c], m = first[c + 1] - first[c];
+        CU_TRY(cudaStreamSynchronize(cs));
+        const uint64_t *po = h_poff + f + c;
+        const size_t packed = po[m];
+        if (host_pos + packed > dst_cap) {
+            for (int k = 0; k < nchunks; k++) cudaStreamSynchronize(w->cs[k]);
+            return fail(MZCU_ERR_DST_TOO_SMALL, "packed output exceeds capacity %zu", dst_cap);
+        }
+        if (packed) CU_TRY(cudaMemcpyAsync(dst + host_pos, w->d_src + h_sbeg[f], packed, cudaMemcpyDeviceToHost, cs));
+        for (int i = 0; i <= m; i++) dst_off_out[f + i] = host_pos + po[i];
+        host_pos += packed;
+    }
+    for (int c = 0; c < nchunks; c++) {
+        CU_TRY(cudaStreamSynchronize(w->cs[c]));
+        CU_TRY(cudaStreamWaitEvent(w->stream, w->tab_ready, 0));
+    }
     CU_TRY(cudaEventRecord(w->ev1, w->stream));
-    CU_TRY(cudaMemcpyAsync(h_poff, d_poff, (size_t)(nblk + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, w->stream));
-    if (crc_out) CU_TRY(cudaMemcpyAsync(crc_out, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-    CU_TRY(cudaStreamSynchronize(w->stream));
-    const size_t packed = h_poff[nblk];
-    if (packed > dst_cap) return fail(MZCU_ERR_DST_TOO_SMALL, "packed output %zu > capacity %zu", packed, dst_cap);
-    if (packed) CU_TRY(cudaMemcpyAsync(dst, w->d_src, packed, cudaMemcpyDeviceToHost, w->stream));
-    for (int i = 0; i <= nblk; i++) dst_off_out[i] = h_poff[i];
     CU_TRY(cudaStreamSynchronize(w->stream));
     cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
     return MZCU_OK;
@@ -563,31 +605,61 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
         h[3 * T + i] = h[2 * T + i] + m;
         dof += (m + 15) & ~size_t(15);
     }
-    if (hi > lo) CU_TRY(cudaMemcpyAsync(w->d_src, src + lo, hi - lo, cudaMemcpyHostToDevice, w->stream));
-    CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 4 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
     int32_t *d_status = reinterpret_cast<int32_t *>(w->d_tab + 4 * T);
     int32_t *h_status = reinterpret_cast<int32_t *>(w->h_tab + 4 * T);
+    uint32_t *d_crc = reinterpret_cast<uint32_t *>(d_status) + T;
+    // Chunk pipeline (see host_encode_blocks_packed): copy in, decode, checksum and copy
+    // out run per chunk on their own streams.  Source ranges must be ascending for the
+    // per-chunk H2D; otherwise the batch goes as one chunk.
+    int nchunks = nblk / kMinChunkBlocks;
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    if (nchunks < 1) nchunks = 1;
+    bool ascending = true;
+    for (int i = 0; i + 1 < nblk; i++)
+        if (h[T + i] > h[i + 1] && h[T + i + 1] > h[i + 1]) ascending = false;
+    if (!ascending) nchunks = 1;
+    int first[kMaxChunks + 1];
+    for (int c = 0; c <= nchunks; c++) first[c] = (int)((int64_t)nblk * c / nchunks);
+    CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 4 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+    CU_TRY(cudaEventRecord(w->tab_ready, w->stream));
     CU_TRY(cudaEventRecord(w->ev0, w->stream));
-    rc = launch_decode(device, nblk, w->d_src, w->d_tab, w->d_tab + T, w->d_dst, w->d_tab + 2 * T, w->d_tab + 3 * T, d_status,
-                       w->stream);
-    if (rc) return rc;
-    if (crc_out) {  // checksum of the decoded blocks while they are resident (reader.go:341-351)
-        uint32_t *d_crc = reinterpret_cast<uint32_t *>(d_status) + T;
-        rc = launch_crc(device, nblk, w->d_dst, w->d_tab + 2 * T, w->d_tab + 3 * T, d_crc, w->stream);
+    for (int c = 0; c < nchunks; c++) {
+        cudaStream_t cs = w->cs[c];
+        const int f = first[c], l = first[c + 1], m = l - f;
+        CU_TRY(cudaStreamWaitEvent(cs, w->tab_ready, 0));
+        // compressed bytes of this chunk: [min begin, max end) over its non-empty ranges
+        uint64_t clo = ~0ull, chi = 0;
+        for (int i = f; i < l; i++)
+            if (h[T + i] > h[i]) {
+                if (h[i] < clo) clo = h[i];
+                if (h[T + i] > chi) chi = h[T + i];
+            }
+        if (nchunks == 1) {
+            clo = 0;
+            chi = hi - lo;
+        }
+        if (chi > clo && clo != ~0ull) CU_TRY(cudaMemcpyAsync(w->d_src + clo, src + lo + clo, chi - clo, cudaMemcpyHostToDevice, cs));
+        rc = launch_decode(device, m, w->d_src, w->d_tab + f, w->d_tab + T + f, w->d_dst, w->d_tab + 2 * T + f,
+                           w->d_tab + 3 * T + f, d_status + f, cs, nblk);
         if (rc) return rc;
-        CU_TRY(cudaMemcpyAsync(crc_out, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-    }
-    CU_TRY(cudaEventRecord(w->ev1, w->stream));
-    CU_TRY(cudaMemcpyAsync(h_status, d_status, (size_t)nblk * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream));
-    if (dense) {
-        size_t total = dend[nblk - 1] - dbeg[0];
-        if (total) CU_TRY(cudaMemcpyAsync(dst + dbeg[0], w->d_dst, total, cudaMemcpyDeviceToHost, w->stream));
-    } else {
-        for (int i = 0; i < nblk; i++) {
-            size_t m = dend[i] - dbeg[i];
-            if (m) CU_TRY(cudaMemcpyAsync(dst + dbeg[i], w->d_dst + h[2 * T + i], m, cudaMemcpyDeviceToHost, w->stream));
+        if (crc_out) {  // checksum of the decoded blocks while they are resident (reader.go:341-351)
+            rc = launch_crc(device, m, w->d_dst, w->d_tab + 2 * T + f, w->d_tab + 3 * T + f, d_crc + f, cs);
+            if (rc) return rc;
+            CU_TRY(cudaMemcpyAsync(crc_out + f, d_crc + f, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+        }
+        CU_TRY(cudaMemcpyAsync(h_status + f, d_status + f, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+        if (dense) {
+            const size_t o0 = dbeg[f] - dbeg[0], o1 = dend[l - 1] - dbeg[0];
+            if (o1 > o0) CU_TRY(cudaMemcpyAsync(dst + dbeg[f], w->d_dst + o0, o1 - o0, cudaMemcpyDeviceToHost, cs));
+        } else {
+            for (int i = f; i < l; i++) {
+                size_t mm = dend[i] - dbeg[i];
+                if (mm) CU_TRY(cudaMemcpyAsync(dst + dbeg[i], w->d_dst + h[2 * T + i], mm, cudaMemcpyDeviceToHost, cs));
+            }
         }
     }
+    for (int c = 0; c < nchunks; c++) CU_TRY(cudaStreamSynchronize(w->cs[c]));
+    CU_TRY(cudaEventRecord(w->ev1, w->stream));
     CU_TRY(cudaStreamSynchronize(w->stream));
     for (int i = 0; i < nblk; i++) status[i] = h_status[i];
     cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);

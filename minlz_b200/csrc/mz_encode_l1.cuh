@@ -259,6 +259,31 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
     int d = 0;
     bool rematch = false;  // the next batch starts with the re-match probe at s (:222-265)
 
+    // Token emission is deferred by one batch: the probes of the next batch only
+    // need the match end, so their loads are issued first and the token of the
+    // previous match is built and stored while they are in flight.
+    int pe_kind = 0;  // 0 none, 1 copy, 2 literals [pe_ne, pe_base) + copy
+    int pe_ne = 0, pe_base = 0, pe_repeat = 0, pe_end = 0;
+    auto flush_pending = [&]() -> bool {
+        if (pe_kind == 0) return true;
+        const int length = pe_end - pe_base;
+        if (pe_kind == 2 && pe_ne != pe_base) {  // :190-206
+            if (pe_base - pe_ne > P::kMaxFuseLits || pe_repeat < kMinCopy2Offset) {
+                if (d + (pe_end - pe_ne) > dstLimit) return false;
+                d += emit_literal(dst + d, src + pe_ne, pe_base - pe_ne, lane);
+                d += emit_copy(dst + d, pe_repeat, length, lane);
+            } else if (pe_repeat <= kMaxCopy2Offset) {
+                d += emit_copy_lits2(dst + d, src + pe_ne, pe_base - pe_ne, pe_repeat, length, lane);
+            } else {
+                d += emit_copy_lits3(dst + d, src + pe_ne, pe_base - pe_ne, pe_repeat, length, lane);
+            }
+        } else {
+            d += emit_copy(dst + d, pe_repeat, length, lane);
+        }
+        pe_kind = 0;
+        return true;
+    };
+
     // loop-invariant lane roles
     // lane 0: insert-only (s-2)      lane 1: re-match probe (s)
     // lanes 2+4j .. 5+4j: level j -> hash0(t), hash1(t+1), hash2(t+2), repeat probe at t+1
@@ -278,7 +303,6 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         if (rematch) {
             nextEmit = s;
             if (s >= sLimit) break;
-            if (d > dstLimit) return 0;
         }
         const int ne = nextEmit;
         ring.seek(s - 8);
@@ -341,6 +365,10 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         }
         uint32_t rep4 = 0;
         if (isrep) rep4 = ldg_u32_unaligned(src + p - repeat);
+
+        // the loads are in flight: emit the previous match now
+        if (!flush_pending()) return 0;
+        if (rematch && d > dstLimit) return 0;  // :229
 
         // in-flight forwarding: the latest earlier insert (serial order = lane order) on my slot
         const unsigned ins_mask = __ballot_sync(kFullMask, inserts);
@@ -467,23 +495,15 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                 s = min(extend_forward8(src, sc, sc - repeat, n - 8, lane), q_stop);
             }
         }
-        const int length = s - base;
-        if (win_lvl != -2 && ne != base) {
-            if (base - ne > P::kMaxFuseLits || repeat < kMinCopy2Offset) {
-                if (d + (s - ne) > dstLimit) return 0;
-                d += emit_literal(dst + d, src + ne, base - ne, lane);
-                d += emit_copy(dst + d, repeat, length, lane);
-            } else if (repeat <= kMaxCopy2Offset) {
-                d += emit_copy_lits2(dst + d, src + ne, base - ne, repeat, length, lane);
-            } else {
-                d += emit_copy_lits3(dst + d, src + ne, base - ne, repeat, length, lane);
-            }
-        } else {
-            d += emit_copy(dst + d, repeat, length, lane);
-        }
+        pe_kind = win_lvl == -2 ? 1 : 2;
+        pe_ne = ne;
+        pe_base = base;
+        pe_repeat = repeat;
+        pe_end = s;
         rematch = true;
     }
 
+    if (!flush_pending()) return 0;
     // emitRemainder (encode_l1.go:268-282)
     if (nextEmit < n) {
         if (d + n - nextEmit > dstLimit) return 0;
