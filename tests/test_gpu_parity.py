@@ -312,3 +312,71 @@ def test_encode_packed_host_api(oracle):
     _, doff = _cat([raws[i] for i in keep])
     out, status = mz.decode_blocks(csrc, csoff, doff)
     assert not status.any() and out.tobytes() == b"".join(raws[i] for i in keep)
+
+
+def test_concurrent_callers(oracle):
+    """The seam must tolerate concurrent calls from arbitrary threads
+    (writer.go:670 spawns one goroutine per block; SURVEY 8b threading row)."""
+    import threading
+    rng = np.random.default_rng(21)
+    inputs = [patterns.generate_test_data(200000 + 1000 * i) for i in range(4)] + \
+             [rng.integers(0, 8, 150000, dtype=np.uint8).tobytes() for _ in range(4)]
+    want = [(oracle.encode(d, 1), oracle.encode(d, 2)) for d in inputs]
+    errors = []
+
+    def worker(k):
+        try:
+            for it in range(6):
+                d = inputs[(k + it) % len(inputs)]
+                w1, w2 = want[(k + it) % len(inputs)]
+                e1 = mz.Encode(None, d, 1)
+                e2 = mz.Encode(None, d, 2)
+                if e1 != w1 or e2 != w2:
+                    errors.append("encode mismatch in thread %d" % k)
+                if mz.Decode(None, e1) != d or mz.Decode(None, w2) != d:
+                    errors.append("decode mismatch in thread %d" % k)
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=240)
+        assert not t.is_alive(), "worker hung"
+    assert not errors, errors[:3]
+
+
+def test_random_structures_roundtrip(oracle):
+    """fuzz_test.go:31 FuzzEncodingBlocks in spirit: random mixtures of literals,
+    short/long repeats and far copies at random sizes; encoder bytes == oracle,
+    decoder output == input, for both levels, all in two batched calls."""
+    rng = np.random.default_rng(99)
+    blocks = []
+    for _ in range(160):
+        n = int(rng.choice([17, 100, 4000, 65536, 65537, 150000, 400000]))
+        n += int(rng.integers(0, 50))
+        alpha = int(rng.choice([2, 4, 16, 256]))
+        base = rng.integers(0, alpha, n, dtype=np.uint8)
+        for _ in range(int(rng.integers(0, 30))):   # paste earlier slices forward
+            ln = int(rng.integers(4, min(n // 2, 5000)))
+            a = int(rng.integers(0, n - ln))
+            b = int(rng.integers(0, n - ln))
+            base[b:b + ln] = base[a:a + ln]
+        blocks.append(base.tobytes())
+    src, soff = _cat(blocks)
+    for level in (1, 2):
+        dst, doff, out_len = mz.encode_blocks(src, soff, level)
+        streams, raws = [], []
+        for i, data in enumerate(blocks):
+            want = oracle.encode_block(data, level)
+            got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
+            assert got == want, (level, i, len(data))
+            if got:
+                streams.append(got)
+                raws.append(data)
+        csrc, csoff = _cat(streams)
+        _, cdoff = _cat(raws)
+        out, status = mz.decode_blocks(csrc, csoff, cdoff)
+        assert not status.any()
+        assert out.tobytes() == b"".join(raws)
