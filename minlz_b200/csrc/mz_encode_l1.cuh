@@ -150,6 +150,21 @@ struct __align__(32) Slot {
 };
 constexpr int kSnapFwd = 24;  // forward bytes held in a slot
 
+// One slot = one 32-byte DRAM sector, moved with Blackwell's 256-bit global
+// accesses (LDG.E.ENL2.256 / STG.E.ENL2.256): a single request per probe, and a
+// full-sector write per insert (no read-for-ownership of a half-written sector).
+__device__ __forceinline__ void slot_load(const Slot *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // ---- per-warp ring of source bytes around the cursor ------------------------
 constexpr int kRingBytes = 1024;
 constexpr int kRingWords = kRingBytes / 4;
@@ -245,11 +260,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         const uint4 ia = make_uint4(0, 0, w0[1], w0[2]);
         const uint4 ib = make_uint4(w0[3], w0[4], w0[5], w0[6]);
         const int slots = 1 << P::kTableBits;
-        for (int i = lane; i < slots; i += 32) {
-            uint4 *q = reinterpret_cast<uint4 *>(table + i);
-            q[0] = ia;
-            q[1] = ib;
-        }
+        for (int i = lane; i < slots; i += 32) slot_store(table + i, ia, ib);
         __syncwarp();
     }
 
@@ -358,11 +369,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
 
         // one 32-byte sector per probing lane; the repeat probe reads the source
         uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
-        if (reads) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(table + h);
-            ea = q[0];
-            eb = q[1];
-        }
+        if (reads) slot_load(table + h, ea, eb);
         uint32_t rep4 = 0;
         if (isrep) rep4 = ldg_u32_unaligned(src + p - repeat);
 
@@ -437,9 +444,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             }
             const unsigned wm = __ballot_sync(kFullMask, w);
             if (w && (same & wm & later) == 0) {  // a later insert on the same slot wins
-                uint4 *q = reinterpret_cast<uint4 *>(table + h);
-                q[0] = make_uint4((uint32_t)p, W[0], W[1], W[2]);
-                q[1] = make_uint4(W[3], W[4], W[5], W[6]);
+                slot_store(table + h, make_uint4((uint32_t)p, W[0], W[1], W[2]), make_uint4(W[3], W[4], W[5], W[6]));
             }
             __syncwarp();
         }
