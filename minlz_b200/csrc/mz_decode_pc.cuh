@@ -291,28 +291,30 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             uint32_t flags = 0;
             bool cut = false;
             const uint32_t s_first = (uint32_t)p_s;
+            // end of stream is noticed at the start of a round (decode.go:615 is checked
+            // by the copier that owns the output cursor)
+            if (!p_done && p_s >= p_slen) {
+                p_done = true;
+                flags = kBatchEnded;
+            }
             uint64_t w8 = ring_load(p_lead + p_s);
             bool w_ok = ring_ok_at(p_lead + p_s);
+            // One token per lane per step.  No votes and no warp-level early exits in here:
+            // every instruction on this path is paid by every block of the CTA on every
+            // token.  Rare cases (bytes not yet in the ring, extended lengths) are plain
+            // divergent branches.
+#pragma unroll 2
             for (int k = 0; k < kDecTok; k++) {
-                const bool act = !p_done && !cut;
-                if (!__any_sync(kFullMask, act)) break;
-                const bool at_end = p_s >= p_slen;
-                const bool live = act && !at_end;
-                if (__any_sync(kFullMask, live && !w_ok)) {  // first round / after a long literal run
-                    if (live && !w_ok) w8 = ldg_window(p_sp, p_s, p_slen);
-                }
+                const bool live = !p_done && !cut && p_s < p_slen;
+                if (live && !w_ok) w8 = ldg_window(p_sp, p_s, p_slen);  // first round / after a long literal run
                 const uint32_t lo = (uint32_t)w8;
                 const uint32_t e = st->lut[lo & 0xff];
-                const bool c3x = (lo & 7) == 7 && ((lo >> 5) & 63) > 60;  // copy3 with extended length
-                const bool slow = (e & 0x80) != 0 || c3x;
                 int adv = (int)(e & 0x7f);
                 bool lng = false;
-                if (__any_sync(kFullMask, live && slow)) {
-                    if (live && slow) {
-                        const PTok t = parse_token_bf(w8);
-                        adv = (int)(t.hdr + t.lit);
-                        lng = t.lit > kDecShort || t.mlen > kDecShort;
-                    }
+                if (live && ((e & 0x80) != 0 || ((lo & 7) == 7 && ((lo >> 5) & 63) > 60))) {  // extended length
+                    const PTok t = parse_token_bf(w8);
+                    adv = (int)(t.hdr + t.lit);
+                    lng = t.lit > kDecShort || t.mlen > kDecShort;
                 }
                 // header and literals must lie inside the stream (decode.go:221,410 src side)
                 const bool bad = adv > p_slen - p_s;
@@ -326,10 +328,11 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     my[1 * kDecTok + cnt] = lo;
                     my[2 * kDecTok + cnt] = (uint32_t)(w8 >> 32);
                 }
-                flags |= (act && at_end) ? kBatchEnded : 0u;
-                flags |= (live && bad) ? kBatchBad : 0u;
-                flags |= (emit && lng) ? kBatchLong : 0u;
-                p_done = p_done || (act && at_end) || (live && bad);
+                if (live && bad) {
+                    flags |= kBatchBad;
+                    p_done = true;
+                }
+                if (emit && lng) flags |= kBatchLong;
                 cut = cut || (live && !bad && lng);
                 p_s = emit ? s_next : p_s;
                 cnt += emit ? 1 : 0;
@@ -349,7 +352,11 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             uint8_t *stage = copier_mem + (size_t)cw * (kDecStage + kDecLitStage + kDecScratch);
             uint8_t *lstage = stage + kDecStage;
             uint8_t *scratch = lstage + kDecLitStage;
+#ifdef MZ_EXPERIMENT_NO_COPY
+            for (int slot = nslots; slot < nslots; slot += kDecCopiers) {
+#else
             for (int slot = cw; slot < nslots; slot += kDecCopiers) {
+#endif
                 const uint32_t cword = st->count[rb][slot];
                 if (cword == 0 || st->dead[slot]) continue;
                 int n = (int)(cword & 0xff);
