@@ -43,13 +43,14 @@
 namespace mz {
 
 constexpr int kDecSlots = 32;      // block slots per CTA (one parser lane each)
-constexpr int kDecCopiers = 14;    // copier warps per CTA
+constexpr int kDecCopiers = 28;    // copier warps per CTA
 // Warp w runs on scheduler w % 4.  The parser (warp 0) is the serial pole of the CTA, so it
 // gets scheduler 0 to itself: warps 4, 8, 12, ... only wait at the round barrier.
-constexpr int kDecWarps = 1 + kDecCopiers + (kDecCopiers + 2) / 3;
+constexpr bool kDecParserAlone = 1 + kDecCopiers + (kDecCopiers + 2) / 3 <= 32;
+constexpr int kDecWarps = kDecParserAlone ? 1 + kDecCopiers + (kDecCopiers + 2) / 3 : 1 + kDecCopiers;
 constexpr int kDecThreads = kDecWarps * 32;
 constexpr int kDecTok = 32;        // tokens per batch
-constexpr int kDecShort = 64;      // max literal / match length of a "short" token
+constexpr int kDecShort = 40;      // max literal / match length of a "short" token
 constexpr int kDecStage = kDecTok * 2 * kDecShort + 32;       // output image of a batch (+ alignment slack)
 constexpr int kDecLitStage = kDecTok * (8 + kDecShort) + 48;  // stream span of a batch
 constexpr int kDecScratch = 32 * 48 + 16;                     // per-lane 48-byte gather landing zone
@@ -346,9 +347,9 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             // every block of this CTA is finished
             const bool some = __any_sync(kFullMask, cnt > 0 || flags != 0);
             if (lane == 0) produced[wb] = some ? 1 : 0;
-        } else if (round > 0 && (warp & 3) != 0 && warp - 1 - (warp >> 2) < kDecCopiers) {
+        } else if (round > 0 && (!kDecParserAlone || ((warp & 3) != 0 && warp - 1 - (warp >> 2) < kDecCopiers))) {
             // ================= COPIERS =================
-            const int cw = warp - 1 - (warp >> 2);
+            const int cw = kDecParserAlone ? warp - 1 - (warp >> 2) : warp - 1;
             uint8_t *stage = copier_mem + (size_t)cw * (kDecStage + kDecLitStage + kDecScratch);
             uint8_t *lstage = stage + kDecStage;
             uint8_t *scratch = lstage + kDecLitStage;
