@@ -303,10 +303,16 @@ def main():
         hc = np.zeros(nb + 1, dtype=np.uint64)
         hst = np.zeros(nb, dtype=np.int32)
 
+        e2e_parts = {"enc": 0.0, "dec": 0.0}
+
         def e2e_step():
             # host blocks -> packed token streams on the host -> host blocks again
+            t0_ = time.perf_counter()
             cb_ = mz.encode_blocks_packed_into(n_src, hs, n_comp, hc, args.level, device=local)
+            t1_ = time.perf_counter()
             mz.decode_blocks_into(n_comp, hc, n_dec, hs, hst, device=local)
+            e2e_parts["enc"] += t1_ - t0_
+            e2e_parts["dec"] += time.perf_counter() - t1_
             return cb_
 
         for _ in range(min(args.warmup, 2)):
@@ -314,6 +320,7 @@ def main():
         assert np.array_equal(n_dec, n_src) and not hst.any()
         if dist is not None:
             dist.barrier()
+        e2e_parts["enc"] = e2e_parts["dec"] = 0.0
         t0 = time.perf_counter()
         ek = max(1, min(K, 3))
         for _ in range(ek):
@@ -328,6 +335,7 @@ def main():
                "h2d_bytes_per_step": int(nb * bs + cb + 2 * 8 * (nb + 1) * 2),
                "d2h_bytes_per_step": int(cb + nb * bs + 8 * nb),
                "blocks_per_step": nb, "ms_per_step": round(dt * 1e3, 3),
+               "encode_call_ms": round(e2e_parts["enc"] / ek * 1e3, 3), "decode_call_ms": round(e2e_parts["dec"] / ek * 1e3, 3),
                "api": "mzcu_encode_blocks_packed + mzcu_decode_blocks (host pointers, pinned)"}
 
     if rank != 0:

@@ -492,7 +492,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         {
             // Go: s = base+4, then 8-byte chunks while s <= n-8 (:181-188)
             int q_stop = base + 4;
-            if (q_stop <= n - 8) q_stop += ((n - 8 - q_stop) / 8 + 1) * 8;
+            if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
             if (wf < kSnapFwd) {
                 s = min(base + known, q_stop);
             } else {
