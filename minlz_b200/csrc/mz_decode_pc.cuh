@@ -457,6 +457,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 // very start of a block, where those bytes belong to a neighbour).
                 const bool head_ok = x0 > 0;
                 if (lane == 0 && shift != 0 && head_ok) cp_async16(stage, dp + x0 - shift);
+                asm volatile("cp.async.commit_group;\n" ::: "memory");  // group 1: stream span + head chunk
                 // 2. back-reference gathers of tokens whose source is complete (ends before
                 //    this span): up to 32 source bytes = three aligned 16-byte chunks per lane
                 const uint32_t m = dpos + lit;    // output position of the match
@@ -475,7 +476,8 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     if (need > 16) cp_async16(myscr + 16, reinterpret_cast<const void *>(ga + 16));
                     if (need > 32) cp_async16(myscr + 32, reinterpret_cast<const void *>(ga + 32));
                 }
-                cp_async_wait_all();
+                asm volatile("cp.async.commit_group;\n" ::: "memory");  // group 2: back-reference gathers
+                asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // the span has landed; gathers still fly
                 __syncwarp();
                 const uint32_t T = shift + (dpos - x0);  // stage offset of this token's output
                 // 3. literals: lstage -> stage, 16 bytes per pass
@@ -488,6 +490,8 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     }
                 }
                 // 4. independent matches: scratch -> stage; 32 source bytes per gather
+                cp_async_wait_all();
+                __syncwarp();
                 {
                     const uint32_t Tm = T + lit;
                     for (uint32_t done = 0;;) {
@@ -522,11 +526,18 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     const uint32_t tsrc = __shfl_sync(kFullMask, srcpos, t);
                     const uint32_t tlen = __shfl_sync(kFullMask, mlen, t);
                     const uint32_t toff = __shfl_sync(kFullMask, off, t);
-                    for (uint32_t i = lane; i < tlen; i += 32) {
-                        const uint32_t j = toff >= tlen ? i : i % toff;  // overlapping: replicate the pattern
-                        const uint32_t q = tsrc + j;
-                        const uint8_t v = q >= x0 ? stage[shift + (q - x0)] : dp[q];
-                        stage[shift + (tm - x0) + i] = v;
+                    if (toff >= tlen) {
+                        for (uint32_t i = lane; i < tlen; i += 32) {
+                            const uint32_t q = tsrc + i;
+                            const uint8_t v = q >= x0 ? stage[shift + (q - x0)] : dp[q];
+                            stage[shift + (tm - x0) + i] = v;
+                        }
+                    } else {  // overlapping: replicate the `toff`-byte pattern
+                        for (uint32_t i = lane; i < tlen; i += 32) {
+                            const uint32_t q = tsrc + i % toff;
+                            const uint8_t v = q >= x0 ? stage[shift + (q - x0)] : dp[q];
+                            stage[shift + (tm - x0) + i] = v;
+                        }
                     }
                     __syncwarp();
                 }
