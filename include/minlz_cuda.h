@@ -37,6 +37,7 @@ extern "C" {
 #define MZCU_MAX_BLOCK_SIZE (8 << 20)
 
 /* encode.go:20-42 levels (only the levels on the hot path are accepted) */
+#define MZCU_LEVEL_SUPERFAST (-1) /* encode_l0.go  encodeBlockFast */
 #define MZCU_LEVEL_UNCOMPRESSED 0
 #define MZCU_LEVEL_FASTEST 1  /* encode_l1.go  encodeBlock        */
 #define MZCU_LEVEL_BALANCED 2 /* encode_l2.go  encodeBlockBetter  */

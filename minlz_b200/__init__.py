@@ -20,6 +20,7 @@ from . import _lib
 
 MaxBlockSize = 8 << 20  # minlz.go:24
 
+LevelSuperFast = -1
 LevelUncompressed = 0  # encode.go:20-42
 LevelFastest = 1
 LevelBalanced = 2
@@ -97,7 +98,7 @@ def Encode(dst, src, level):
     n = MaxEncodedLen(s.size)
     if n < 0:
         raise ErrTooLarge()
-    if level not in (LevelUncompressed, LevelFastest, LevelBalanced):
+    if level not in (LevelSuperFast, LevelUncompressed, LevelFastest, LevelBalanced):
         if s.size < 16:
             return b"\x00" + (b"\x00" + s.tobytes() if s.size else b"")  # encode.go:83-85 runs before the level switch
         raise ErrInvalidLevel()
@@ -117,7 +118,7 @@ def TryEncode(dst, src, level):
     """encode.go:168-207: None when Go returns nil."""
     s = _np(src)
     n = MaxEncodedLen(s.size)
-    if n < 0 or s.size < 16 or level not in (LevelFastest, LevelBalanced):
+    if n < 0 or s.size < 16 or level not in (LevelSuperFast, LevelFastest, LevelBalanced):
         return None
     out = np.empty(n, dtype=np.uint8)
     r = _lib.load().mzcu_try_encode(out.ctypes.data, out.size, _ptr(s), s.size, level)
@@ -174,7 +175,7 @@ def _offsets(sizes):
 
 def EncodeBatch(blocks, level, device=-1):
     """Encode() over a list of inputs with one GPU launch; returns list of bytes."""
-    if level not in (LevelUncompressed, LevelFastest, LevelBalanced):
+    if level not in (LevelSuperFast, LevelUncompressed, LevelFastest, LevelBalanced):
         raise ErrInvalidLevel()
     arrs = [_np(b) for b in blocks]
     for a in arrs:

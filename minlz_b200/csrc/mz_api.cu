@@ -110,7 +110,7 @@ int init_device(int device) {
             delete h;
         }
         if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.enc_l1_ctas_per_sm, mz::encode_l1_kernel,
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.enc_l1_ctas_per_sm, mz::encode_l1_kernel<false>,
                                                               mz::kEncL1Warps * 32, 0);
         if (st.enc_l1_ctas_per_sm < 1) st.enc_l1_ctas_per_sm = 1;
         if (e == cudaSuccess)
@@ -180,7 +180,7 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
     DeviceState &st = g_dev[device];
     int *counter = st.counters + (st.next_counter.fetch_add(1) % kCounterSlots);
     CU_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-    if (level == MZCU_LEVEL_FASTEST) {
+    if (level == MZCU_LEVEL_FASTEST || level == MZCU_LEVEL_SUPERFAST) {
         // one block per warp, all resident: grid = min(blocks, what fits on the chip)
         int grid = (nblk + mz::kEncL1Warps - 1) / mz::kEncL1Warps;
         int resident = st.num_sms * st.enc_l1_ctas_per_sm;
@@ -188,8 +188,12 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
         TableWs ws;
         int rc = acquire_tables(st, (size_t)grid * mz::kEncL1Warps * mz::kEncL1WsBytesPerWarp, &ws);
         if (rc) return rc;
-        mz::encode_l1_kernel<<<grid, mz::kEncL1Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len, counter,
-                                                                       static_cast<mz::Slot *>(ws.ptr));
+        if (level == MZCU_LEVEL_FASTEST)
+            mz::encode_l1_kernel<false><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len,
+                                                                                  counter, static_cast<mz::Slot *>(ws.ptr));
+        else
+            mz::encode_l1_kernel<true><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len,
+                                                                                 counter, static_cast<mz::Slot *>(ws.ptr));
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaEventRecord(ws.done, stream);
         release_tables(st, ws);
@@ -408,7 +412,7 @@ int64_t store_uncompressed(uint8_t *dst, size_t cap, const uint8_t *src, size_t 
 int host_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                        const uint64_t *dst_off, uint32_t *out_len) {
     if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !out_len))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
-    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+    if (level != MZCU_LEVEL_SUPERFAST && level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
         return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
     if (nblk == 0) return MZCU_OK;
     device = resolve_device(device);
@@ -475,7 +479,7 @@ int host_encode_blocks(int device, int level, int nblk, const uint8_t *src, cons
 int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                               size_t dst_cap, uint64_t *dst_off_out, uint32_t *crc_out) {
     if (nblk < 0 || !dst_off_out || (nblk > 0 && (!src_off || !dst))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
-    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+    if (level != MZCU_LEVEL_SUPERFAST && level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
         return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
     dst_off_out[0] = 0;
     if (nblk == 0) return MZCU_OK;
@@ -712,7 +716,7 @@ int mzcu_encode_blocks_dev(int device, int level, int nblk, const uint8_t *src, 
                            const uint64_t *dst_off, uint32_t *out_len, void *stream) {
     if (nblk < 0 || (nblk > 0 && (!src || !src_off || !dst || !dst_off || !out_len)))
         return fail(MZCU_ERR_INVALID_ARG, "null argument");
-    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+    if (level != MZCU_LEVEL_SUPERFAST && level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
         return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
     device = resolve_device(device);
     if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
@@ -808,7 +812,7 @@ int mzcu_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t 
 int mzcu_encode_batch(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                       const uint64_t *dst_off, uint64_t *enc_len) {
     if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !enc_len))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
-    if (level != MZCU_LEVEL_UNCOMPRESSED && level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
+    if (level != MZCU_LEVEL_SUPERFAST && level != MZCU_LEVEL_UNCOMPRESSED && level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED)
         return fail(MZCU_ERR_INVALID_LEVEL, "invalid level %d", level);
     // Per block: dst = 0x00 uvarint(n) tokens  (encode.go:87-90), with the
     // token stream produced right behind the header.
@@ -910,7 +914,7 @@ int64_t mzcu_try_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t
     // encode.go:168-207: nil unless compressible and d+n < len(src)
     int64_t need = mzcu_max_encoded_len((int64_t)n);
     if (need < 0 || (int64_t)dst_cap < need || n < 16) return 0;
-    if (level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED) return 0;
+    if (level != MZCU_LEVEL_SUPERFAST && level != MZCU_LEVEL_FASTEST && level != MZCU_LEVEL_BALANCED) return 0;
     std::vector<uint8_t> tmp(n + 18);
     uint64_t so[2] = {0, n}, dof[2] = {0, n + 2};
     uint32_t out = 0;

@@ -60,6 +60,7 @@ __device__ __forceinline__ uint32_t hash5(uint64_t u, int h) {
 __device__ __forceinline__ uint32_t hash6(uint64_t u, int h) {
     return (uint32_t)(((u << 16) * 227718039650203ull) >> (64 - h));
 }
+__device__ __forceinline__ uint32_t hash8(uint64_t u, int h) { return (uint32_t)((u * 0xcf1bbcdcb7a56463ull) >> (64 - h)); }
 __device__ __forceinline__ uint32_t hash7(uint64_t u, int h) {
     return (uint32_t)(((u << 8) * 58295818150454627ull) >> (64 - h));
 }

@@ -116,14 +116,33 @@ __device__ __forceinline__ int emit_copy_lits3(uint8_t *dst, const uint8_t *lits
     return n + nlits;
 }
 
+// LevelFastest: encode_l1.go:39-283 (large) and :285-524 (<= 64 KiB)
 template <bool kSmall>
 struct L1Params {
     static constexpr int kTableBits = kSmall ? 13 : 15;
     static constexpr int kSkipLog = kSmall ? 5 : 6;
+    static constexpr int kStep = 4;
     static constexpr int kMaxFuseLits = kSmall ? kMaxCopy2Lits : kMaxCopy3Lits;
+    static constexpr int kMinMatch = 4;         // candidates are verified on 4 bytes
+    static constexpr bool kBackExtend = true;   // :169-172
+    __device__ static __forceinline__ int dst_limit(int n) { return n - (n >> 5) - 6; }
     __device__ static __forceinline__ uint32_t hash(uint64_t u) {
         return kSmall ? hash5(u, kTableBits) : hash6(u, kTableBits);
     }
+};
+
+// LevelSuperFast: encode_l0.go:32-279 (large) and :281-522 (<= 64 KiB).  Same walk
+// with an 8-byte minimum match, hash8, no backward extension, extension from +8.
+template <bool kSmall>
+struct L0Params {
+    static constexpr int kTableBits = kSmall ? 12 : 13;
+    static constexpr int kSkipLog = kSmall ? 4 : 5;
+    static constexpr int kStep = kSmall ? 4 : 5;
+    static constexpr int kMaxFuseLits = kSmall ? kMaxCopy2Lits : kMaxCopy3Lits;
+    static constexpr int kMinMatch = 8;
+    static constexpr bool kBackExtend = false;  // encode_l0.go:164 `for false && ...`
+    __device__ static __forceinline__ int dst_limit(int n) { return kSmall ? n - (n >> 4) - 32 : n - (n >> 3) - 6; }
+    __device__ static __forceinline__ uint32_t hash(uint64_t u) { return hash8(u, kTableBits); }
 };
 
 // Backward extension, restating
@@ -242,12 +261,11 @@ __device__ __forceinline__ int pick(const int (&t)[kMaxLevels + 1], int i) {
 }
 
 // Encodes one block with one warp.  Returns bytes written or 0.
-template <bool kSmall>
+template <class P>
 __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Slot *table, uint32_t *ring_mem,
                                const int lane) {
-    using P = L1Params<kSmall>;
     const int sLimit = n - kInputMargin;
-    const int dstLimit = n - (n >> 5) - 6;
+    const int dstLimit = P::dst_limit(n);
     const int fill_limit = (n + 64 + kRingChunk - 1) & ~(kRingChunk - 1);
 
     SrcRing ring{ring_mem, src, n, 0};
@@ -328,7 +346,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             bool open = true;
 #pragma unroll
             for (int j = 0; j < kMaxLevels; j++) {
-                int nxt = t[j] + ((t[j] - ne) >> P::kSkipLog) + 4;
+                int nxt = t[j] + ((t[j] - ne) >> P::kSkipLog) + P::kStep;
                 t[j + 1] = nxt;
                 if (open && j < want) {
                     if (nxt > sLimit) {
@@ -404,7 +422,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         if (reads) {
             const int anchor = lvl >= 0 ? pick(t, lvl) : s;
             const bool in_range = lvl >= 0 ? cand >= anchor - kMaxCopy3Offset : s - cand <= kMaxCopy3Offset;
-            if (in_range && cd[0] == W[1]) {
+            if (in_range && cd[0] == W[1] && (P::kMinMatch == 4 || cd[1] == W[2])) {
                 ok = true;
                 fbytes = prefix24(cd, W + 1);
                 const uint32_t x = cb ^ W[0];
@@ -482,7 +500,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             known = wf;
         } else {
             const int ps = pick(t, win_lvl) + wsub;
-            const int room = min(wcand, ps - ne);  // :169-172
+            const int room = P::kBackExtend ? min(wcand, ps - ne) : 0;  // :169-172
             int back = min(wb, room);
             if (back == 4 && room > 4) back += extend_backward(src, wcand - 4, ps - 4, ne, lane);
             base = ps - back;
@@ -490,13 +508,13 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             known = back + wf;
         }
         {
-            // Go: s = base+4, then 8-byte chunks while s <= n-8 (:181-188)
-            int q_stop = base + 4;
+            // Go: s = base + min match, then 8-byte chunks while s <= n-8 (:181-188)
+            int q_stop = base + P::kMinMatch;
             if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
             if (wf < kSnapFwd) {
                 s = min(base + known, q_stop);
             } else {
-                const int sc = base + 4 + 8 * ((known - 4) >> 3);
+                const int sc = base + P::kMinMatch + 8 * ((known - P::kMinMatch) >> 3);
                 s = min(extend_forward8(src, sc, sc - repeat, n - 8, lane), q_stop);
             }
         }
@@ -519,6 +537,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
 
 // Persistent kernel: every warp pulls block indices from *counter and owns the
 // workspace slice `tables + global_warp * 1 MiB`.
+template <bool kSuperFast>
 __global__ void __launch_bounds__(kEncL1Warps * 32)
 encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
@@ -539,8 +558,12 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
         int res = 0;
         if (n64 >= kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {
             const int n = (int)n64;
-            res = n <= 65536 ? encode_l1_block<true>(dp, sp, n, table, rings[warp], lane)
-                             : encode_l1_block<false>(dp, sp, n, table, rings[warp], lane);
+            if (kSuperFast)
+                res = n <= 65536 ? encode_l1_block<L0Params<true>>(dp, sp, n, table, rings[warp], lane)
+                                 : encode_l1_block<L0Params<false>>(dp, sp, n, table, rings[warp], lane);
+            else
+                res = n <= 65536 ? encode_l1_block<L1Params<true>>(dp, sp, n, table, rings[warp], lane)
+                                 : encode_l1_block<L1Params<false>>(dp, sp, n, table, rings[warp], lane);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();

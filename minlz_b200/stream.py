@@ -23,8 +23,8 @@ import io
 import numpy as np
 
 from . import _lib
-from . import (ErrCorrupt, ErrInvalidLevel, ErrTooLarge, ErrUnsupported, LevelBalanced, LevelFastest, LevelUncompressed,
-               MinLZError, _raise)
+from . import (ErrCorrupt, ErrInvalidLevel, ErrTooLarge, ErrUnsupported, LevelBalanced, LevelFastest, LevelSuperFast,
+               LevelUncompressed, MinLZError, _raise)
 
 # minlz.go:77-131
 MAGIC_CHUNK = b"\xff\x06\x00\x00MinLz"
@@ -86,8 +86,8 @@ def make_header(block_size):
 
 def WriterLevel(n):
     def f(w):
-        if n not in (LevelUncompressed, LevelFastest, LevelBalanced):
-            raise ErrInvalidLevel()  # LevelSuperFast / LevelSmallest are not on the accelerated path
+        if n not in (LevelSuperFast, LevelUncompressed, LevelFastest, LevelBalanced):
+            raise ErrInvalidLevel()  # LevelSmallest is not on the accelerated path
         w.level = n
     return f
 

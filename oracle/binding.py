@@ -33,7 +33,7 @@ def lib():
         u8p, u64p, u32p, i32p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
         L.mzo_max_encoded_len.restype = C.c_int64
         L.mzo_max_encoded_len.argtypes = [C.c_int64]
-        for f in (L.mzo_encode_block_l1, L.mzo_encode_block_l2):
+        for f in (L.mzo_encode_block_l0, L.mzo_encode_block_l1, L.mzo_encode_block_l2):
             f.restype = C.c_int64
             f.argtypes = [u8p, u8p, C.c_size_t]
         L.mzo_decode_block.restype = C.c_int
@@ -84,7 +84,7 @@ def encode_block(src, level):
     """encodeBlock / encodeBlockBetter: token stream without header; b'' = 0 (incompressible)."""
     s = _in(src)
     dst = np.empty(s.size + 64, dtype=np.uint8)
-    f = lib().mzo_encode_block_l1 if level == 1 else lib().mzo_encode_block_l2
+    f = {-1: lib().mzo_encode_block_l0, 1: lib().mzo_encode_block_l1, 2: lib().mzo_encode_block_l2}[level]
     n = f(dst.ctypes.data, _ptr(s), s.size)
     return dst[:n].tobytes()
 

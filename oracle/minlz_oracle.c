@@ -48,6 +48,7 @@ static inline uint32_t hash4(uint64_t u, int h) { return ((uint32_t)u * 26544357
 static inline uint32_t hash5(uint64_t u, int h) { return (uint32_t)(((u << 24) * 889523592379ull) >> (64 - h)); }
 static inline uint32_t hash6(uint64_t u, int h) { return (uint32_t)(((u << 16) * 227718039650203ull) >> (64 - h)); }
 static inline uint32_t hash7(uint64_t u, int h) { return (uint32_t)(((u << 8) * 58295818150454627ull) >> (64 - h)); }
+static inline uint32_t hash8(uint64_t u, int h) { return (uint32_t)((u * 0xcf1bbcdcb7a56463ull) >> (64 - h)); }
 
 static inline uint32_t hashN(uint64_t u, int h, int nbytes) {
     switch (nbytes) {
@@ -416,6 +417,142 @@ int64_t mzo_encode_block_l1(uint8_t *dst, const uint8_t *src, size_t n) {
     return encode_l1(dst, src, (int)n, 15, 6, 6, kMaxCopy3Lits);
 }
 
+/* ---- L0 "SuperFast": encode_l0.go:32-279 (tableBits 13, skipLog 5, step 5,
+ *      dstLimit len - len>>3 - 6, fuse<=3) and :281-522 (tableBits 12, skipLog 4,
+ *      step 4, dstLimit len - len>>4 - 32, fuse<=4).  Same skeleton as L1 with an
+ *      8-byte minimum match (hash8, full 8-byte compares), no backward extension
+ *      (encode_l0.go:164 `for false && ...`) and extension from +8. ---------- */
+static int64_t encode_l0(uint8_t *dst, const uint8_t *src, int n, int tableBits, int skipLog, int step, int dstLimit,
+                         int maxFuseLits) {
+    uint32_t *table = (uint32_t *)calloc((size_t)1 << tableBits, sizeof(uint32_t));
+    if (!table) return 0;
+    const int sLimit = n - kInputMargin;
+    int nextEmit = 0;
+    int s = 1;
+    uint64_t cv = ld64(src, s);
+    int repeat = 1;
+    int d = 0;
+    int candidate;
+
+    for (;;) {
+        candidate = 0;
+        for (;;) {
+            int nextS = s + ((s - nextEmit) >> skipLog) + step; /* :60 */
+            if (nextS > sLimit) goto emit_remainder;
+            int minSrcPos = s - kMaxCopy3Offset;
+            uint32_t hash0 = hash8(cv, tableBits);
+            uint64_t cv1 = ld64(src, s + 1);
+            uint32_t hash1 = hash8(cv1, tableBits);
+            candidate = (int)table[hash0];
+            int candidate2 = (int)table[hash1];
+            table[hash0] = (uint32_t)s;
+            table[hash1] = (uint32_t)(s + 1);
+            uint64_t cv2 = ld64(src, s + 2);
+            uint32_t hash2 = hash8(cv2, tableBits);
+
+            if ((uint32_t)cv1 == ld32(src, s - repeat + 1)) { /* :77 */
+                int base = s + 1;
+                for (int i = base - repeat; base > nextEmit && i > 0 && src[i - 1] == src[base - 1];) {
+                    i--;
+                    base--;
+                }
+                if (d + (base - nextEmit) > dstLimit) {
+                    free(table);
+                    return 0;
+                }
+                d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(base - nextEmit));
+                int cand = s - repeat + 4 + 1;
+                s += 4 + 1;
+                s = extend8(src, s, cand, sLimit);
+                d += mzo_emit_repeat(dst + d, s - base);
+                nextEmit = s;
+                if (s >= sLimit) goto emit_remainder;
+                cv = ld64(src, s);
+                continue;
+            }
+            if (candidate >= minSrcPos && cv == ld64(src, candidate)) break; /* :142 */
+            candidate = (int)table[hash2];
+            if (candidate2 >= minSrcPos && cv1 == ld64(src, candidate2)) {
+                table[hash2] = (uint32_t)(s + 2);
+                candidate = candidate2;
+                s++;
+                break;
+            }
+            table[hash2] = (uint32_t)(s + 2);
+            if (candidate >= minSrcPos && cv2 == ld64(src, candidate)) {
+                s += 2;
+                break;
+            }
+            cv = ld64(src, nextS);
+            s = nextS;
+        }
+        /* no backward extension (:164) */
+        int base = s;
+        repeat = base - candidate;
+        s += 8; /* :174 */
+        candidate += 8;
+        s = extend8(src, s, candidate, n - 8);
+        int length = s - base;
+        if (nextEmit != base) {
+            if (base - nextEmit > maxFuseLits || repeat < kMinCopy2Offset) {
+                if (d + (s - nextEmit) > dstLimit) {
+                    free(table);
+                    return 0;
+                }
+                d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(base - nextEmit));
+                d += mzo_emit_copy(dst + d, repeat, length);
+            } else if (repeat <= kMaxCopy2Offset) {
+                d += mzo_emit_copy_lits2(dst + d, src + nextEmit, base - nextEmit, repeat, length);
+            } else {
+                d += mzo_emit_copy_lits3(dst + d, src + nextEmit, base - nextEmit, repeat, length);
+            }
+        } else {
+            d += mzo_emit_copy(dst + d, repeat, length);
+        }
+        for (;;) { /* :218-261 */
+            nextEmit = s;
+            if (s >= sLimit) goto emit_remainder;
+            uint64_t x = ld64(src, s - 2);
+            if (d > dstLimit) {
+                free(table);
+                return 0;
+            }
+            uint32_t m2Hash = hash8(x, tableBits);
+            x = ld64(src, s);
+            uint32_t currHash = hash8(x, tableBits);
+            candidate = (int)table[currHash];
+            table[m2Hash] = (uint32_t)(s - 2);
+            table[currHash] = (uint32_t)s;
+            if (s - candidate > kMaxCopy3Offset || x != ld64(src, candidate)) {
+                cv = ld64(src, s + 1);
+                s++;
+                break;
+            }
+            repeat = s - candidate;
+            base = s;
+            s += 8;
+            candidate += 8;
+            s = extend8(src, s, candidate, n - 8);
+            d += mzo_emit_copy(dst + d, repeat, s - base);
+        }
+    }
+emit_remainder:
+    free(table);
+    if (nextEmit < n) {
+        if (d + n - nextEmit > dstLimit) return 0;
+        d += mzo_emit_literal(dst + d, src + nextEmit, (size_t)(n - nextEmit));
+    }
+    return d;
+}
+
+/* asm_none.go:33-43 encodeBlockFast */
+int64_t mzo_encode_block_l0(uint8_t *dst, const uint8_t *src, size_t n) {
+    if (n < kMinNonLiteralBlockSize || n > MZO_MAX_BLOCK_SIZE) return 0;
+    int nn = (int)n;
+    if (n <= 65536) return encode_l0(dst, src, nn, 12, 4, 4, nn - (nn >> 4) - 32, kMaxCopy2Lits);
+    return encode_l0(dst, src, nn, 13, 5, 5, nn - (nn >> 3) - 6, kMaxCopy3Lits);
+}
+
 /* ---- L2: encode_l2.go:61-338 (long 17 bit hash7 / short 14 bit hash4) and
  *          encode_l2.go:343-596 (long 15 bit hash6 / short 12 bit hash4).
  * As for L1, one parameterised body: the 64K variant drops guards that cannot
@@ -781,7 +918,7 @@ int64_t mzo_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, i
      * The block encoders need headroom beyond n+2 while probing, as in Go
      * (dst[d:] where len(dst)=n+2, bails keep d below dstLimit). */
     if ((int64_t)dst_cap < maxlen) return MZO_ERR_DST_TOO_SMALL;
-    if (level != 0 && level != 1 && level != 2) return MZO_ERR_INVALID_LEVEL;
+    if (level != -1 && level != 0 && level != 1 && level != 2) return MZO_ERR_INVALID_LEVEL;
     if (level == 0) return encode_uncompressed(dst, dst_cap, src, n);
     dst[0] = 0;
     int d = 1 + put_uvarint(dst + 1, n);
@@ -790,7 +927,7 @@ int64_t mzo_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t n, i
      * buffer with slack so the oracle never depends on that. */
     uint8_t *tmp = (uint8_t *)malloc(n + 64);
     if (!tmp) return MZO_ERR_DST_TOO_SMALL;
-    int64_t m = level == 1 ? mzo_encode_block_l1(tmp, src, n) : mzo_encode_block_l2(tmp, src, n);
+    int64_t m = level == 1 ? mzo_encode_block_l1(tmp, src, n) : level == 2 ? mzo_encode_block_l2(tmp, src, n) : mzo_encode_block_l0(tmp, src, n);
     if (m > 0) {
         memcpy(dst + d, tmp, (size_t)m);
         free(tmp);
@@ -805,12 +942,12 @@ int64_t mzo_try_encode(uint8_t *dst, size_t dst_cap, const uint8_t *src, size_t 
     int64_t maxlen = mzo_max_encoded_len((int64_t)n);
     if (maxlen < 0 || (int64_t)dst_cap < maxlen) return 0;
     if (n < kMinNonLiteralBlockSize) return 0;
-    if (level != 1 && level != 2) return 0;
+    if (level != -1 && level != 1 && level != 2) return 0;
     dst[0] = 0;
     int d = 1 + put_uvarint(dst + 1, n);
     uint8_t *tmp = (uint8_t *)malloc(n + 64);
     if (!tmp) return 0;
-    int64_t m = level == 1 ? mzo_encode_block_l1(tmp, src, n) : mzo_encode_block_l2(tmp, src, n);
+    int64_t m = level == 1 ? mzo_encode_block_l1(tmp, src, n) : level == 2 ? mzo_encode_block_l2(tmp, src, n) : mzo_encode_block_l0(tmp, src, n);
     if (m > 0 && d + m < (int64_t)n) {
         memcpy(dst + d, tmp, (size_t)m);
         free(tmp);
@@ -958,7 +1095,7 @@ static void *batch_worker(void *arg) {
         if (j->decode) {
             j->status[i] = mzo_decode_block(d, dn, s, sn);
         } else {
-            int64_t m = j->level == 1 ? mzo_encode_block_l1(d, s, sn) : mzo_encode_block_l2(d, s, sn);
+            int64_t m = j->level == 1 ? mzo_encode_block_l1(d, s, sn) : j->level == 2 ? mzo_encode_block_l2(d, s, sn) : mzo_encode_block_l0(d, s, sn);
             j->out_len[i] = (uint32_t)m;
         }
     }
@@ -979,7 +1116,7 @@ static int run_batch(batch_job *j, int nthreads) {
 
 int mzo_encode_batch_mt(int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                         const uint64_t *dst_off, uint32_t *out_len, int nthreads) {
-    if (level != 1 && level != 2) return MZO_ERR_INVALID_LEVEL;
+    if (level != -1 && level != 1 && level != 2) return MZO_ERR_INVALID_LEVEL;
     batch_job j = {level, nblk, src, src_off, dst, dst_off, out_len, NULL, 0, 0};
     return run_batch(&j, nthreads);
 }

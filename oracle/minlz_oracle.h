@@ -9,6 +9,7 @@
  * What it restates (reference = minio/minlz, pure-Go "noasm" path):
  *   decoder   decode.go:178-622  (minLZDecodeGo), cross-read with
  *             internal/reference/decoder.go:26-373
+ *   L0        encode_l0.go:32-279 (encodeFastBlockGo), :281-522 (...Go64K)
  *   L1        encode_l1.go:39-283 (encodeBlockGo), :285-524 (encodeBlockGo64K)
  *   L2        encode_l2.go:61-338 (encodeBlockBetterGo), :343-596 (...Go64K)
  *   emitters  asm_none.go:84-323, encode.go:247-282
@@ -55,6 +56,7 @@ int mzo_emit_copy_lits3(uint8_t *dst, const uint8_t *lits, int nlits, int offset
 
 /* asm_none.go:51-76 dispatch: returns bytes written, 0 = not compressible.
  * dst must hold mzo_max_encoded_len(n) bytes; header is NOT written. */
+int64_t mzo_encode_block_l0(uint8_t *dst, const uint8_t *src, size_t n); /* LevelSuperFast, encode_l0.go */
 int64_t mzo_encode_block_l1(uint8_t *dst, const uint8_t *src, size_t n);
 int64_t mzo_encode_block_l2(uint8_t *dst, const uint8_t *src, size_t n);
 

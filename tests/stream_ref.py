@@ -25,7 +25,7 @@ def chunk(ctype, body):
 
 def data_chunk(block, level):
     crc = oracle.crc(block).to_bytes(4, "little")
-    tok = oracle.encode_block(block, level) if level in (1, 2) else b""
+    tok = oracle.encode_block(block, level) if level in (-1, 1, 2) else b""
     if tok:
         return chunk(0x02, crc + uvarint(len(block)) + tok)
     return chunk(0x01, crc + block)

@@ -21,7 +21,7 @@ def _inputs(name):
 
 
 def _roundtrip(oracle, data):
-    for level in (1, 2):
+    for level in (-1, 1, 2):
         enc = oracle.encode(data, level)
         assert isinstance(enc, bytes)
         assert len(enc) <= oracle.max_encoded_len(len(data))

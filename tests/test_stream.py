@@ -72,7 +72,7 @@ def _payloads():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("level", [0, 1, 2])
+@pytest.mark.parametrize("level", [-1, 0, 1, 2])
 @pytest.mark.parametrize("block_size", [4 << 10, 64 << 10, 1 << 20])
 def test_writer_bytes_equal_reference_framing(oracle, level, block_size):
     """Writer output == framing restatement over oracle-encoded blocks, byte for byte."""
