@@ -188,6 +188,7 @@ __device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 
 constexpr int kRingBytes = 1024;
 constexpr int kRingWords = kRingBytes / 4;
 constexpr int kRingChunk = 256;
+constexpr int kRingMirror = 16;  // the first 64 bytes are stored again behind the end: windows never wrap
 
 struct SrcRing {
     uint32_t *ring;  // kRingWords words of shared memory owned by this warp
@@ -210,6 +211,10 @@ struct SrcRing {
             int w = (pos >> 2) & (kRingWords - 1);
             ring[w] = (uint32_t)v;
             ring[w + 1] = (uint32_t)(v >> 32);
+            if (w < kRingMirror) {
+                ring[kRingWords + w] = (uint32_t)v;
+                ring[kRingWords + w + 1] = (uint32_t)(v >> 32);
+            }
             filled += kRingChunk;
             __syncwarp();
         }
@@ -220,61 +225,77 @@ struct SrcRing {
         if (lo >= filled) filled = lo & ~(kRingChunk - 1);
     }
 
-    // out[0..8) = src[b .. b+32) (b may be negative at the very start of a
+    // out[0..7) = src[b .. b+28) (b may be negative at the very start of a
     // block; those bytes are never used).
-    __device__ __forceinline__ void fetch32(int b, uint32_t out[8]) const {
-        int a = b >> 2;
-        unsigned sh = (unsigned)(b & 3) * 8;
-        uint32_t w[9];
+    __device__ __forceinline__ void fetch28(int b, uint32_t out[7]) const {
+        const uint32_t *q = ring + ((b >> 2) & (kRingWords - 1));
+        const unsigned sh = (unsigned)(b & 3) * 8;
+        uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 9; j++) w[j] = ring[(a + j) & (kRingWords - 1)];
+        for (int j = 0; j < 8; j++) w[j] = q[j];
 #pragma unroll
-        for (int j = 0; j < 8; j++) out[j] = __funnelshift_r(w[j], w[j + 1], sh);
+        for (int j = 0; j < 7; j++) out[j] = __funnelshift_r(w[j], w[j + 1], sh);
     }
 };
 
-// bytes of common prefix of two 24-byte strings held as 6 words each
-__device__ __forceinline__ int prefix24(const uint32_t *x, const uint32_t *y) {
-    int r = 24;
-#pragma unroll
-    for (int j = 5; j >= 0; j--) {
-        uint32_t d = x[j] ^ y[j];
-        if (d) r = 4 * j + ((__ffs(d) - 1) >> 3);
-    }
-    return r;
-}
-
 constexpr int kEncL1Warps = 4;  // warps per CTA
+#ifndef MZ_ENC_L1_MIN_CTAS
+#define MZ_ENC_L1_MIN_CTAS 8  // 32 warps per SM: 148 x 32 >= 4096 blocks in flight
+#endif
 constexpr int kEncL1SlotsPerWarp = 1 << 15;
 constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot);  // 1 MiB
 
-// Speculative search steps evaluated per round trip.
-constexpr int kSpecAfterRematch = 1;  // behind a re-match probe
-constexpr int kSpecSearch = 2;        // in a pure search batch
-constexpr int kMaxLevels = 2;
-
-__device__ __forceinline__ int pick(const int (&t)[kMaxLevels + 1], int i) {
-    int r = t[0];
+// 24-bit mask, bit k set when byte k of the two 24-byte strings (6 words each)
+// differs.  Per word: "has non-zero byte" flags at bits 7/15/23/31, gathered
+// into a nibble by one multiply (the partial products do not collide).
+__device__ __forceinline__ uint32_t nzmask24(const uint32_t *x, const uint32_t *y) {
+    uint32_t acc = 0;
 #pragma unroll
-    for (int j = 1; j <= kMaxLevels; j++) r = i == j ? t[j] : r;
-    return r;
+    for (int j = 5; j >= 0; j--) {
+        const uint32_t d = x[j] ^ y[j];
+        const uint32_t t = (d | ((d & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+        acc = acc * 16u + ((t * 0x204081u) >> 28);
+    }
+    return acc;
 }
 
+// Result of one table probe as the serial algorithm would see it.
+struct Probe {
+    bool hit;     // candidate in range and equal on the minimum match length
+    bool fw;      // candidate is an insert of this same batch (cand/nz/bb below are valid)
+    int cand;
+    uint32_t nz;  // nzmask24(src[cand..], src[pos..])
+    int bb;       // equal bytes going back from cand-1 / pos-1, <= 4
+};
+
 // Encodes one block with one warp.  Returns bytes written or 0.
+//
+// One iteration of the outer loop is one BATCH = one DRAM round trip: lane L
+// owns position wbase + L, loads its 32 source bytes from the ring, hashes
+// them and fetches its table slot (position + snapshot of the bytes around it).
+// After the round trip every lane knows whether ITS position would verify
+// against the pre-batch table, how far the match runs (<= 24 bytes forward,
+// <= 4 back) and whether it passes the repeat check.  The warp then replays the
+// reference's control flow (search steps, back-to-back re-match probes, repeat
+// checks) over these 32 answers with warp-uniform bit tests, consuming as many
+// steps as fall inside the window, and finally writes back the table inserts
+// the replay performed.  Inserts of the same batch that alias a later probe's
+// slot are forwarded from the ring (`dup` / Probe::fw).
 template <class P>
 __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Slot *table, uint32_t *ring_mem,
                                const int lane) {
     const int sLimit = n - kInputMargin;
     const int dstLimit = P::dst_limit(n);
     const int fill_limit = (n + 64 + kRingChunk - 1) & ~(kRingChunk - 1);
+    constexpr uint32_t kMinMask = P::kMinMatch == 8 ? 0xffu : 0xfu;
 
     SrcRing ring{ring_mem, src, n, 0};
     ring.ensure(min(2 * kRingChunk, fill_limit), lane);
 
     // Empty slots read as candidate 0 (encode_l1.go:52,86): position 0 and its bytes.
     {
-        uint32_t w0[8];
-        ring.fetch32(-4, w0);
+        uint32_t w0[7];
+        ring.fetch28(-4, w0);
         const uint4 ia = make_uint4(0, 0, w0[1], w0[2]);
         const uint4 ib = make_uint4(w0[3], w0[4], w0[5], w0[6]);
         const int slots = 1 << P::kTableBits;
@@ -283,18 +304,16 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
     }
 
     int nextEmit = 0;
-    int s = 1;
+    int s = 1;             // cursor: the re-match position, or the search position t
     int repeat = 1;
     int d = 0;
-    bool rematch = false;  // the next batch starts with the re-match probe at s (:222-265)
+    bool rematch = false;  // the cursor is in the re-match loop (:222-265)
 
-    // Token emission is deferred by one batch: the probes of the next batch only
-    // need the match end, so their loads are issued first and the token of the
-    // previous match is built and stored while they are in flight.
+    // Token emission is deferred by one match: the last match of a batch is
+    // emitted while the next batch's loads are in flight.
     int pe_kind = 0;  // 0 none, 1 copy, 2 literals [pe_ne, pe_base) + copy
     int pe_ne = 0, pe_base = 0, pe_repeat = 0, pe_end = 0;
     auto flush_pending = [&]() -> bool {
-        if (pe_kind == 0) return true;
         const int length = pe_end - pe_base;
         if (pe_kind == 2 && pe_ne != pe_base) {  // :190-206
             if (pe_base - pe_ne > P::kMaxFuseLits || pe_repeat < kMinCopy2Offset) {
@@ -313,220 +332,210 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         return true;
     };
 
-    // loop-invariant lane roles
-    // lane 0: insert-only (s-2)      lane 1: re-match probe (s)
-    // lanes 2+4j .. 5+4j: level j -> hash0(t), hash1(t+1), hash2(t+2), repeat probe at t+1
-    const bool lvl_lane = lane >= 2 && lane < 2 + 4 * kMaxLevels;
-    const int my_lvl = (lane - 2) >> 2;
-    const int sub = lvl_lane ? (lane - 2) & 3 : 0;
-    const int padd = sub == 3 ? 1 : sub;
-    unsigned vis_base = 0;
-    if (lvl_lane && sub < 3) {
-        vis_base = (1u << (2 + 4 * my_lvl)) - 1;           // the re-match lanes and every earlier level
-        if (sub == 2) vis_base |= 3u << (2 + 4 * my_lvl);  // hash2 is read after hash0/hash1 were written
-    }
-    const unsigned later = ~((2u << lane) - 1u);
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned above = ~((2u << lane) - 1u);
+    bool done = false;  // reached emitRemainder
 
-    for (;;) {
-        // ---------------- plan the batch ----------------
-        if (rematch) {
-            nextEmit = s;
-            if (s >= sLimit) break;
-        }
-        const int ne = nextEmit;
-        ring.seek(s - 8);
-        ring.ensure(min(s + 320, fill_limit), lane);
-        // level j probes t[j], t[j]+1, t[j]+2; t[j+1] is its nextS (:79)
-        int t[kMaxLevels + 1];
-        t[0] = rematch ? s + 1 : s;
-        int nlev = 0;
-        bool hit_end = false;  // the first level not probed starts with nextS > sLimit (:80)
-        {
-            const int want = rematch ? kSpecAfterRematch : kSpecSearch;
-            bool open = true;
-#pragma unroll
-            for (int j = 0; j < kMaxLevels; j++) {
-                int nxt = t[j] + ((t[j] - ne) >> P::kSkipLog) + P::kStep;
-                t[j + 1] = nxt;
-                if (open && j < want) {
-                    if (nxt > sLimit) {
-                        hit_end = true;
-                        open = false;
-                    } else if (t[j] + 2 + 28 <= ring.filled) {
-                        nlev = j + 1;
-                    } else {
-                        open = false;
-                    }
-                } else {
-                    open = false;
-                }
-            }
-        }
-        if (!rematch && nlev == 0) {
-            if (hit_end) break;
-            return 0;  // unreachable: ensure() always covers one level
-        }
+    while (!done) {
+        // ---------------- one round trip for the whole window ----------------
+        const int wbase = rematch ? s - 2 : s;
+        // When the skip distance is long (incompressible data) only the first search
+        // step can fall in the window: do not fetch slots nobody will consume.
+        const int K = (!rematch && ((s - nextEmit) >> P::kSkipLog) >= 24) ? 8 : 32;
+        ring.seek(wbase - 8);
+        ring.ensure(min(wbase + 320, fill_limit), lane);
+        const int p = wbase + lane;
+        const bool active = lane < K;
 
-        // ---------------- this batch's lane roles ----------------
-        int lvl = -1, p = s;
-        if (lane < 2) {
-            lvl = rematch ? -2 : -1;
-            p = lane == 0 ? s - 2 : s;
-        } else if (lvl_lane && my_lvl < nlev) {
-            lvl = my_lvl;
-            p = pick(t, my_lvl) + padd;
-        }
-        const bool active = lvl != -1;
-        const bool isrep = lvl >= 0 && sub == 3;
-        const bool inserts = active && !isrep;
-        const bool reads = inserts && lane != 0;
-
-        uint32_t W[8];  // src[p-4 .. p+28)
-        ring.fetch32(p - 4, W);
+        uint32_t W[7];  // src[p-4 .. p+24)
+        ring.fetch28(p - 4, W);
         const uint32_t h = P::hash((uint64_t)W[2] << 32 | W[1]);
-
-        // one 32-byte sector per probing lane; the repeat probe reads the source
         uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
-        if (reads) slot_load(table + h, ea, eb);
+        if (active) slot_load(table + h, ea, eb);
+        const bool rep_lane = active && p >= repeat;
         uint32_t rep4 = 0;
-        if (isrep) rep4 = ldg_u32_unaligned(src + p - repeat);
+        if (rep_lane) rep4 = ldg_u32_unaligned(src + p - repeat);
 
-        // the loads are in flight: emit the previous match now
-        if (!flush_pending()) return 0;
-        if (rematch && d > dstLimit) return 0;  // :229
+        // the loads are in flight: emit the last match of the previous batch
+        if (pe_kind && !flush_pending()) return 0;
 
-        // in-flight forwarding: the latest earlier insert (serial order = lane order) on my slot
-        const unsigned ins_mask = __ballot_sync(kFullMask, inserts);
-        const unsigned same = __match_any_sync(kFullMask, inserts ? h : 0x80000000u + lane) & ins_mask;
-        const unsigned vis = reads ? vis_base & same : 0;
-        int cand = (int)ea.x;
-        uint32_t cb = ea.y;
-        uint32_t cd[6] = {ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
-        const bool fwd = vis != 0;
-        if (__any_sync(kFullMask, fwd)) {  // rare: short-period data
-            const int from = fwd ? 31 - __clz(vis) : lane;
-            const int cpos = __shfl_sync(kFullMask, p, from);
-            if (fwd) {
-                cand = cpos;
-                uint32_t V[8];
-                ring.fetch32(cand - 4, V);
-                cb = V[0];
-#pragma unroll
-                for (int j = 0; j < 6; j++) cd[j] = V[j + 1];
-            }
+        const unsigned same = __match_any_sync(kFullMask, h);
+        const unsigned dup = __ballot_sync(kFullMask, (same & below) != 0);
+
+        const int cand = (int)ea.x;
+        uint32_t nz;
+        {
+            const uint32_t cd[6] = {ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+            nz = nzmask24(cd, W + 1);
         }
-
-        // ---------------- evaluate ----------------
-        bool ok = false;
-        int fbytes = 0, bbytes = 0;
-        if (reads) {
-            const int anchor = lvl >= 0 ? pick(t, lvl) : s;
-            const bool in_range = lvl >= 0 ? cand >= anchor - kMaxCopy3Offset : s - cand <= kMaxCopy3Offset;
-            if (in_range && cd[0] == W[1] && (P::kMinMatch == 4 || cd[1] == W[2])) {
-                ok = true;
-                fbytes = prefix24(cd, W + 1);
-                const uint32_t x = cb ^ W[0];
-                bbytes = x ? __clz(x) >> 3 : 4;
-            }
-        } else if (isrep) {
-            ok = rep4 == W[1];
+        const uint32_t xb = ea.y ^ W[0];
+        const int bb = xb ? __clz(xb) >> 3 : 4;
+        const bool eqm = active && (nz & kMinMask) == 0;
+        const int dist = p - cand;
+        // search probe j of a step sees minSrcPos = t - maxCopy3Offset (:83): dist <= max + j
+        const unsigned E0 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset);
+        unsigned E1 = E0, E2 = E0;
+        if (n > kMaxCopy3Offset) {
+            E1 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset + 1);
+            E2 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset + 2);
         }
-        const unsigned okm = __ballot_sync(kFullMask, ok);
+        const unsigned Brep = __ballot_sync(kFullMask, rep_lane && rep4 == W[1]);
 
-        // serial priority: re-match probe; then per level repeat, hash0, hash1, hash2
-        int win = -1;
-        int win_lvl = nlev;  // nlev: every probed level missed
-        if (rematch && (okm & 2u)) {
-            win = 1;
-            win_lvl = -2;
-        } else {
-#pragma unroll
-            for (int j = kMaxLevels - 1; j >= 0; j--) {
-                const unsigned g = (okm >> (2 + 4 * j)) & 15u;
-                if (j < nlev && g) {
-                    win = 2 + 4 * j + ((g & 8u) ? 3 : (g & 1u) ? 0 : (g & 2u) ? 1 : 2);
-                    win_lvl = j;
+        // ---------------- replay the serial walk over the window ----------------
+        unsigned ins = 0;     // lanes whose position was inserted, in serial order = lane order
+        bool rep_snap = false;  // repeat checks come from the last match's snapshot (Rnz, Rps)
+        uint32_t Rnz = 0;
+        int Rps = 0;
+
+        auto probe = [&](int L, unsigned E) -> Probe {
+            Probe r;
+            r.hit = (E >> L) & 1u;
+            r.fw = false;
+            r.cand = 0;
+            r.nz = 0;
+            r.bb = 0;
+            if ((dup >> L) & 1u) {  // rare: an earlier lane of the window hashes to the same slot
+                const unsigned sm = __shfl_sync(kFullMask, same, L);
+                const unsigned f = sm & ins & ((1u << L) - 1u);
+                if (f) {  // the latest such insert is what the table holds by now
+                    r.fw = true;
+                    r.cand = wbase + 31 - __clz(f);
+                    uint32_t A[7], B[7];
+                    ring.fetch28(wbase + L - 4, A);
+                    ring.fetch28(r.cand - 4, B);
+                    r.nz = nzmask24(B + 1, A + 1);
+                    const uint32_t x = A[0] ^ B[0];
+                    r.bb = x ? __clz(x) >> 3 : 4;
+                    r.hit = (r.nz & kMinMask) == 0;
                 }
             }
-        }
-        const int wsub = win >= 2 ? (win - 2) & 3 : 0;
+            return r;
+        };
 
-        // ---------------- write back the inserts that really happened ----------------
-        {
-            bool w = false;
-            if (inserts) {
-                if (lvl == -2) w = true;                       // :238-239 run before the test
-                else if (win_lvl == -2) w = false;
-                else if (lvl < win_lvl) w = true;
-                else if (lvl == win_lvl) w = sub < 2 || wsub == 1 || wsub == 2;  // hash2: :152/:157 only
+        for (;;) {
+            // termination and window checks first: a batch that ends here keeps its
+            // last match pending for the next batch's load shadow
+            const int L = s - wbase;
+            const int nextS = s + ((s - nextEmit) >> P::kSkipLog) + P::kStep;  // :79 (search mode)
+            if (rematch) {
+                nextEmit = s;
+                if (s >= sLimit) {
+                    done = true;
+                    break;
+                }
+                if (L >= K) break;
+            } else {
+                if (nextS > sLimit) {
+                    done = true;
+                    break;
+                }
+                if (L + 2 >= K) break;
+                if (rep_snap && s + 1 - Rps > kSnapFwd - 4) break;  // repeat check not covered by the snapshot
             }
-            const unsigned wm = __ballot_sync(kFullMask, w);
-            if (w && (same & wm & later) == 0) {  // a later insert on the same slot wins
-                slot_store(table + h, make_uint4((uint32_t)p, W[0], W[1], W[2]), make_uint4(W[3], W[4], W[5], W[6]));
+            if (pe_kind && !flush_pending()) return 0;
+            int mps;  // position of the verified probe
+            Probe m;
+            bool from_rematch;
+            if (rematch) {
+                if (d > dstLimit) return 0;  // :229
+                m = probe(L, E0);            // read before this step's inserts (:236-239)
+                ins |= 5u << (L - 2);
+                if (!m.hit) {
+                    rematch = false;
+                    s++;
+                    continue;
+                }
+                mps = s;
+                from_rematch = true;
+            } else {
+                const int t = s;
+                // repeat check at t+1 (:94)
+                const bool rhit = rep_snap ? ((Rnz >> (t + 1 - Rps)) & 0xfu) == 0 : (Brep >> (L + 1)) & 1u;
+                const Probe r0 = probe(L, E0);
+                const Probe r1 = probe(L + 1, E1);
+                ins |= 3u << L;
+                if (rhit) {
+                    int base = t + 1;
+                    base -= extend_backward(src, base - repeat, base, nextEmit, lane);
+                    if (d + (base - nextEmit) > dstLimit) return 0;
+                    d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane);
+                    s = extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane);
+                    d += emit_repeat(dst + d, s - base, lane);
+                    nextEmit = s;
+                    if (s >= sLimit) {
+                        done = true;
+                        break;
+                    }
+                    continue;
+                }
+                if (r0.hit) {
+                    m = r0;
+                    mps = t;
+                } else {
+                    ins |= 4u << L;  // :152 / :157
+                    if (r1.hit) {
+                        m = r1;
+                        mps = t + 1;
+                    } else {
+                        m = probe(L + 2, E2);  // read after the inserts of t and t+1 (:150)
+                        if (!m.hit) {
+                            s = nextS;
+                            continue;
+                        }
+                        mps = t + 2;
+                    }
+                }
+                from_rematch = false;
             }
-            __syncwarp();
-        }
 
-        if (win < 0) {  // every probed step missed: continue the search behind them
-            s = pick(t, nlev);
-            rematch = false;
-            if (hit_end) break;
-            continue;
-        }
-
-        // ---------------- process the hit ----------------
-        const int wcand = __shfl_sync(kFullMask, cand, win);
-        const int wf = __shfl_sync(kFullMask, fbytes, win);
-        const int wb = __shfl_sync(kFullMask, bbytes, win);
-
-        if (win_lvl >= 0 && wsub == 3) {  // repeat at t+1 (encode_l1.go:94-145)
-            const int tt = pick(t, win_lvl);
-            int base = tt + 1;
-            base -= extend_backward(src, base - repeat, base, ne, lane);
-            if (d + (base - ne) > dstLimit) return 0;
-            d += emit_literal(dst + d, src + ne, base - ne, lane);
-            s = extend_forward8(src, tt + 5, tt + 5 - repeat, sLimit, lane);
-            d += emit_repeat(dst + d, s - base, lane);
-            nextEmit = s;
-            if (s >= sLimit) break;
-            rematch = false;
-            continue;
-        }
-
-        int base, known;  // match start, bytes known equal from it
-        if (win_lvl == -2) {
-            base = s;
-            repeat = s - wcand;
-            known = wf;
-        } else {
-            const int ps = pick(t, win_lvl) + wsub;
-            const int room = P::kBackExtend ? min(wcand, ps - ne) : 0;  // :169-172
-            int back = min(wb, room);
-            if (back == 4 && room > 4) back += extend_backward(src, wcand - 4, ps - 4, ne, lane);
-            base = ps - back;
-            repeat = ps - wcand;
-            known = back + wf;
-        }
-        {
+            // ---------------- a verified candidate at mps ----------------
+            if (!m.fw) {
+                const int L = mps - wbase;
+                m.cand = __shfl_sync(kFullMask, cand, L);
+                m.nz = __shfl_sync(kFullMask, nz, L);
+                m.bb = __shfl_sync(kFullMask, bb, L);
+            }
+            const int f = m.nz ? __ffs(m.nz) - 1 : kSnapFwd;
+            int base = mps, known = f;
+            if (!from_rematch && P::kBackExtend) {  // :169-172
+                const int room = min(m.cand, mps - nextEmit);
+                int back = min(m.bb, room);
+                if (back == 4 && room > 4) back += extend_backward(src, m.cand - 4, mps - 4, nextEmit, lane);
+                base = mps - back;
+                known = back + f;
+            }
+            repeat = mps - m.cand;
             // Go: s = base + min match, then 8-byte chunks while s <= n-8 (:181-188)
             int q_stop = base + P::kMinMatch;
             if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
-            if (wf < kSnapFwd) {
-                s = min(base + known, q_stop);
+            int e;
+            if (f < kSnapFwd) {
+                e = min(base + known, q_stop);
             } else {
                 const int sc = base + P::kMinMatch + 8 * ((known - P::kMinMatch) >> 3);
-                s = min(extend_forward8(src, sc, sc - repeat, n - 8, lane), q_stop);
+                e = min(extend_forward8(src, sc, sc - repeat, n - 8, lane), q_stop);
             }
+            pe_kind = from_rematch ? 1 : 2;
+            pe_ne = nextEmit;
+            pe_base = base;
+            pe_repeat = repeat;
+            pe_end = e;
+            rep_snap = true;
+            Rnz = m.nz;
+            Rps = mps;
+            s = e;
+            rematch = true;
         }
-        pe_kind = win_lvl == -2 ? 1 : 2;
-        pe_ne = ne;
-        pe_base = base;
-        pe_repeat = repeat;
-        pe_end = s;
-        rematch = true;
+        if (done) break;
+
+        // ---------------- write back the inserts the replay performed ----------------
+        if (((ins >> lane) & 1u) && (same & ins & above) == 0) {  // a later insert on the same slot wins
+            slot_store(table + h, make_uint4((uint32_t)p, W[0], W[1], W[2]), make_uint4(W[3], W[4], W[5], W[6]));
+        }
+        __syncwarp();
     }
 
-    if (!flush_pending()) return 0;
+    if (pe_kind && !flush_pending()) return 0;
     // emitRemainder (encode_l1.go:268-282)
     if (nextEmit < n) {
         if (d + n - nextEmit > dstLimit) return 0;
@@ -538,11 +547,11 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
 // Persistent kernel: every warp pulls block indices from *counter and owns the
 // workspace slice `tables + global_warp * 1 MiB`.
 template <bool kSuperFast>
-__global__ void __launch_bounds__(kEncL1Warps * 32)
+__global__ void __launch_bounds__(kEncL1Warps * 32, MZ_ENC_L1_MIN_CTAS)
 encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                  uint32_t *__restrict__ out_len, int *counter, Slot *tables) {
-    __shared__ uint32_t rings[kEncL1Warps][kRingWords];
+    __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
