@@ -39,7 +39,7 @@ namespace mz {
 // with the lanes comparing consecutive 8-byte words; the first round uses 4
 // lanes (most matches end within 32 bytes, and the candidate side is a random
 // DRAM sector), later rounds all 32.
-__device__ __forceinline__ int extend_forward8(const uint8_t *src, int s, int cand, int limit, int lane) {
+__device__ __noinline__ int extend_forward8(const uint8_t *src, int s, int cand, int limit, int lane) {
     int width = 4;
     for (;;) {
         int pos = s + 8 * lane;
@@ -63,7 +63,7 @@ __device__ __forceinline__ int extend_forward8(const uint8_t *src, int s, int ca
 
 // Writes the low n bytes of tok at dst (n <= 8), one byte per lane.
 __device__ __forceinline__ void put_token(uint8_t *dst, uint64_t tok, int n, int lane) {
-    if (lane < n) dst[lane] = (uint8_t)(tok >> (8 * lane));
+    if (lane < n) dst[lane] = (uint8_t)__byte_perm((uint32_t)tok, (uint32_t)(tok >> 32), lane);
 }
 
 __device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, int n, int lane) {
@@ -148,7 +148,7 @@ struct L0Params {
 // Backward extension, restating
 //   for cand > 0 && s > floor && src[cand-1] == src[s-1] { cand--; s-- }
 // with one byte pair per lane per round.  Returns the number of steps taken.
-__device__ __forceinline__ int extend_backward(const uint8_t *src, int cand, int s, int floor_, int lane) {
+__device__ __noinline__ int extend_backward(const uint8_t *src, int cand, int s, int floor_, int lane) {
     int total = 0;
     for (;;) {
         int room = min(cand, s - floor_);
@@ -240,7 +240,7 @@ struct SrcRing {
 
 constexpr int kEncL1Warps = 4;  // warps per CTA
 #ifndef MZ_ENC_L1_MIN_CTAS
-#define MZ_ENC_L1_MIN_CTAS 8  // 32 warps per SM: 148 x 32 >= 4096 blocks in flight
+#define MZ_ENC_L1_MIN_CTAS 7  // 28 warps per SM x 148 SMs >= 4096 blocks in flight, 72 registers
 #endif
 constexpr int kEncL1SlotsPerWarp = 1 << 15;
 constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot);  // 1 MiB
@@ -259,28 +259,36 @@ __device__ __forceinline__ uint32_t nzmask24(const uint32_t *x, const uint32_t *
     return acc;
 }
 
-// Result of one table probe as the serial algorithm would see it.
-struct Probe {
-    bool hit;     // candidate in range and equal on the minimum match length
-    bool fw;      // candidate is an insert of this same batch (cand/nz/bb below are valid)
-    int cand;
-    uint32_t nz;  // nzmask24(src[cand..], src[pos..])
-    int bb;       // equal bytes going back from cand-1 / pos-1, <= 4
-};
+// Cold path of a probe whose slot was written earlier in the same batch: the
+// table then holds that insert, whose bytes are still in the ring.  Returns
+// nzmask24(src[cand..], src[pos..]) | back-equal byte count (<= 4) << 24.
+__device__ __noinline__ uint32_t probe_forwarded(const uint32_t *ring_mem, int pos, int cand) {
+    SrcRing ring{const_cast<uint32_t *>(ring_mem), nullptr, 0, 0};
+    uint32_t A[7], B[7];
+    ring.fetch28(pos - 4, A);
+    ring.fetch28(cand - 4, B);
+    const uint32_t x = A[0] ^ B[0];
+    const uint32_t bb = x ? __clz(x) >> 3 : 4;
+    return nzmask24(B + 1, A + 1) | bb << 24;
+}
 
 // Encodes one block with one warp.  Returns bytes written or 0.
 //
 // One iteration of the outer loop is one BATCH = one DRAM round trip: lane L
-// owns position wbase + L, loads its 32 source bytes from the ring, hashes
+// owns position wbase + L, loads its 28 source bytes from the ring, hashes
 // them and fetches its table slot (position + snapshot of the bytes around it).
 // After the round trip every lane knows whether ITS position would verify
 // against the pre-batch table, how far the match runs (<= 24 bytes forward,
 // <= 4 back) and whether it passes the repeat check.  The warp then replays the
 // reference's control flow (search steps, back-to-back re-match probes, repeat
 // checks) over these 32 answers with warp-uniform bit tests, consuming as many
-// steps as fall inside the window, and finally writes back the table inserts
-// the replay performed.  Inserts of the same batch that alias a later probe's
-// slot are forwarded from the ring (`dup` / Probe::fw).
+// steps as fall inside the window; the matches it finds are queued (one per
+// lane) and turned into tokens while the NEXT batch's loads are in flight.
+// Finally the table inserts the replay performed are written back.  Inserts of
+// the same batch that alias a later probe's slot are forwarded from the ring
+// (`dup`, probe_forwarded).  The bail-out tests of the reference (dstLimit)
+// are evaluated by the token writer with the same values of d, one batch late;
+// the result (0 = incompressible) is the same.
 template <class P>
 __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Slot *table, uint32_t *ring_mem,
                                const int lane) {
@@ -304,60 +312,73 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
     }
 
     int nextEmit = 0;
-    int s = 1;             // cursor: the re-match position, or the search position t
+    int s = 1;  // cursor: the re-match position, or the search position t
     int repeat = 1;
     int d = 0;
     bool rematch = false;  // the cursor is in the re-match loop (:222-265)
+    bool done = false;     // reached emitRemainder
 
-    // Token emission is deferred by one match: the last match of a batch is
-    // emitted while the next batch's loads are in flight.
-    int pe_kind = 0;  // 0 none, 1 copy, 2 literals [pe_ne, pe_base) + copy
-    int pe_ne = 0, pe_base = 0, pe_repeat = 0, pe_end = 0;
-    auto flush_pending = [&]() -> bool {
-        const int length = pe_end - pe_base;
-        if (pe_kind == 2 && pe_ne != pe_base) {  // :190-206
-            if (pe_base - pe_ne > P::kMaxFuseLits || pe_repeat < kMinCopy2Offset) {
-                if (d + (pe_end - pe_ne) > dstLimit) return false;
-                d += emit_literal(dst + d, src + pe_ne, pe_base - pe_ne, lane);
-                d += emit_copy(dst + d, pe_repeat, length, lane);
-            } else if (pe_repeat <= kMaxCopy2Offset) {
-                d += emit_copy_lits2(dst + d, src + pe_ne, pe_base - pe_ne, pe_repeat, length, lane);
-            } else {
-                d += emit_copy_lits3(dst + d, src + pe_ne, pe_base - pe_ne, pe_repeat, length, lane);
-            }
-        } else {
-            d += emit_copy(dst + d, pe_repeat, length, lane);
-        }
-        pe_kind = 0;
-        return true;
-    };
+    // queue of this batch's matches, entry i in lane i:
+    // kind 1 copy, 2 literals [ne, base) + copy, 3 literals + repeat
+    int q_kind = 0, q_ne = 0, q_base = 0, q_rep = 0, q_end = 0;
+    int q_cnt = 0;
 
     const unsigned below = (1u << lane) - 1u;
     const unsigned above = ~((2u << lane) - 1u);
-    bool done = false;  // reached emitRemainder
 
-    while (!done) {
+    for (;;) {
         // ---------------- one round trip for the whole window ----------------
         const int wbase = rematch ? s - 2 : s;
         // When the skip distance is long (incompressible data) only the first search
         // step can fall in the window: do not fetch slots nobody will consume.
         const int K = (!rematch && ((s - nextEmit) >> P::kSkipLog) >= 24) ? 8 : 32;
-        ring.seek(wbase - 8);
-        ring.ensure(min(wbase + 320, fill_limit), lane);
         const int p = wbase + lane;
-        const bool active = lane < K;
-
+        const bool active = lane < K && !done;
         uint32_t W[7];  // src[p-4 .. p+24)
-        ring.fetch28(p - 4, W);
-        const uint32_t h = P::hash((uint64_t)W[2] << 32 | W[1]);
+        uint32_t h = 0;
         uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
-        if (active) slot_load(table + h, ea, eb);
-        const bool rep_lane = active && p >= repeat;
         uint32_t rep4 = 0;
-        if (rep_lane) rep4 = ldg_u32_unaligned(src + p - repeat);
+        const bool rep_lane = active && p >= repeat;
+        if (!done) {
+            ring.seek(wbase - 8);
+            ring.ensure(min(wbase + 320, fill_limit), lane);
+            ring.fetch28(p - 4, W);
+            h = P::hash((uint64_t)W[2] << 32 | W[1]);
+            if (active) slot_load(table + h, ea, eb);
+            if (rep_lane) rep4 = ldg_u32_unaligned(src + p - repeat);
+        }
 
-        // the loads are in flight: emit the last match of the previous batch
-        if (pe_kind && !flush_pending()) return 0;
+        // ---------------- the loads are in flight: write the queued tokens ----------------
+        for (int i = 0; i < q_cnt; i++) {
+            const int kind = __shfl_sync(kFullMask, q_kind, i);
+            const int ne = __shfl_sync(kFullMask, q_ne, i);
+            const int base = __shfl_sync(kFullMask, q_base, i);
+            const int rep = __shfl_sync(kFullMask, q_rep, i);
+            const int end = __shfl_sync(kFullMask, q_end, i);
+            const int length = end - base;
+            if (kind == 3) {  // :94-145
+                if (d + (base - ne) > dstLimit) return 0;
+                d += emit_literal(dst + d, src + ne, base - ne, lane);
+                d += emit_repeat(dst + d, length, lane);
+                continue;
+            }
+            if (kind == 2 && ne != base) {  // :190-206
+                if (base - ne > P::kMaxFuseLits || rep < kMinCopy2Offset) {
+                    if (d + (end - ne) > dstLimit) return 0;
+                    d += emit_literal(dst + d, src + ne, base - ne, lane);
+                    d += emit_copy(dst + d, rep, length, lane);
+                } else if (rep <= kMaxCopy2Offset) {
+                    d += emit_copy_lits2(dst + d, src + ne, base - ne, rep, length, lane);
+                } else {
+                    d += emit_copy_lits3(dst + d, src + ne, base - ne, rep, length, lane);
+                }
+            } else {
+                d += emit_copy(dst + d, rep, length, lane);
+            }
+            if (end < sLimit && d > dstLimit) return 0;  // :229, first thing the re-match loop does
+        }
+        q_cnt = 0;
+        if (done) break;
 
         const unsigned same = __match_any_sync(kFullMask, h);
         const unsigned dup = __ballot_sync(kFullMask, (same & below) != 0);
@@ -368,8 +389,10 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             const uint32_t cd[6] = {ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
             nz = nzmask24(cd, W + 1);
         }
-        const uint32_t xb = ea.y ^ W[0];
-        const int bb = xb ? __clz(xb) >> 3 : 4;
+        {
+            const uint32_t xb = ea.y ^ W[0];
+            nz |= (xb ? __clz(xb) >> 3 : 4) << 24;  // back-equal bytes ride in bits 24..26
+        }
         const bool eqm = active && (nz & kMinMask) == 0;
         const int dist = p - cand;
         // search probe j of a step sees minSrcPos = t - maxCopy3Offset (:83): dist <= max + j
@@ -382,41 +405,28 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         const unsigned Brep = __ballot_sync(kFullMask, rep_lane && rep4 == W[1]);
 
         // ---------------- replay the serial walk over the window ----------------
-        unsigned ins = 0;     // lanes whose position was inserted, in serial order = lane order
+        unsigned ins = 0;       // lanes whose position was inserted; serial order = lane order
         bool rep_snap = false;  // repeat checks come from the last match's snapshot (Rnz, Rps)
         uint32_t Rnz = 0;
         int Rps = 0;
 
-        auto probe = [&](int L, unsigned E) -> Probe {
-            Probe r;
-            r.hit = (E >> L) & 1u;
-            r.fw = false;
-            r.cand = 0;
-            r.nz = 0;
-            r.bb = 0;
-            if ((dup >> L) & 1u) {  // rare: an earlier lane of the window hashes to the same slot
-                const unsigned sm = __shfl_sync(kFullMask, same, L);
-                const unsigned f = sm & ins & ((1u << L) - 1u);
-                if (f) {  // the latest such insert is what the table holds by now
-                    r.fw = true;
-                    r.cand = wbase + 31 - __clz(f);
-                    uint32_t A[7], B[7];
-                    ring.fetch28(wbase + L - 4, A);
-                    ring.fetch28(r.cand - 4, B);
-                    r.nz = nzmask24(B + 1, A + 1);
-                    const uint32_t x = A[0] ^ B[0];
-                    r.bb = x ? __clz(x) >> 3 : 4;
-                    r.hit = (r.nz & kMinMask) == 0;
-                }
-            }
-            return r;
+        // Probe of lane L against the table as of `ins_at`: hit flag; when the slot was
+        // written earlier in this batch the candidate is that insert (*fcand, *fnz).
+        auto probe_cold = [&](int L, unsigned ins_at, bool fast_hit, int *fcand, uint32_t *fnz) -> bool {
+            const unsigned sm = __shfl_sync(kFullMask, same, L);
+            const unsigned f = sm & ins_at & ((1u << L) - 1u);
+            *fcand = -1;
+            if (f == 0) return fast_hit;
+            *fcand = wbase + 31 - __clz(f);
+            *fnz = probe_forwarded(ring_mem, wbase + L, *fcand);
+            return (*fnz & kMinMask) == 0;
         };
 
         for (;;) {
-            // termination and window checks first: a batch that ends here keeps its
-            // last match pending for the next batch's load shadow
             const int L = s - wbase;
-            const int nextS = s + ((s - nextEmit) >> P::kSkipLog) + P::kStep;  // :79 (search mode)
+            int mps, fcand = -1;  // position of the verified probe; its forwarded candidate if any
+            uint32_t fnz = 0;
+            bool from_rematch;
             if (rematch) {
                 nextEmit = s;
                 if (s >= sLimit) {
@@ -424,23 +434,10 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                     break;
                 }
                 if (L >= K) break;
-            } else {
-                if (nextS > sLimit) {
-                    done = true;
-                    break;
-                }
-                if (L + 2 >= K) break;
-                if (rep_snap && s + 1 - Rps > kSnapFwd - 4) break;  // repeat check not covered by the snapshot
-            }
-            if (pe_kind && !flush_pending()) return 0;
-            int mps;  // position of the verified probe
-            Probe m;
-            bool from_rematch;
-            if (rematch) {
-                if (d > dstLimit) return 0;  // :229
-                m = probe(L, E0);            // read before this step's inserts (:236-239)
+                bool hit = (E0 >> L) & 1u;  // read before this step's inserts (:236-239)
+                if ((dup >> L) & 1u) hit = probe_cold(L, ins, hit, &fcand, &fnz);
                 ins |= 5u << (L - 2);
-                if (!m.hit) {
+                if (!hit) {
                     rematch = false;
                     s++;
                     continue;
@@ -449,18 +446,33 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                 from_rematch = true;
             } else {
                 const int t = s;
-                // repeat check at t+1 (:94)
-                const bool rhit = rep_snap ? ((Rnz >> (t + 1 - Rps)) & 0xfu) == 0 : (Brep >> (L + 1)) & 1u;
-                const Probe r0 = probe(L, E0);
-                const Probe r1 = probe(L + 1, E1);
-                ins |= 3u << L;
+                const int nextS = t + ((t - nextEmit) >> P::kSkipLog) + P::kStep;  // :79
+                if (nextS > sLimit) {
+                    done = true;
+                    break;
+                }
+                if (L + 2 >= K) break;
+                bool rhit;  // repeat check at t+1 (:94)
+                if (rep_snap) {
+                    const int dl = t + 1 - Rps;
+                    if (dl > kSnapFwd - 4) break;  // not covered by the snapshot: next batch
+                    rhit = ((Rnz >> dl) & 0xfu) == 0;
+                } else {
+                    rhit = (Brep >> (L + 1)) & 1u;
+                }
                 if (rhit) {
+                    ins |= 3u << L;
                     int base = t + 1;
                     base -= extend_backward(src, base - repeat, base, nextEmit, lane);
-                    if (d + (base - nextEmit) > dstLimit) return 0;
-                    d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane);
                     s = extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane);
-                    d += emit_repeat(dst + d, s - base, lane);
+                    if (lane == q_cnt) {
+                        q_kind = 3;
+                        q_ne = nextEmit;
+                        q_base = base;
+                        q_rep = repeat;
+                        q_end = s;
+                    }
+                    q_cnt++;
                     nextEmit = s;
                     if (s >= sLimit) {
                         done = true;
@@ -468,65 +480,91 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                     }
                     continue;
                 }
-                if (r0.hit) {
-                    m = r0;
+                const unsigned x0 = E0 >> L, x1 = E1 >> L, x2 = E2 >> L;
+                bool h0 = x0 & 1u, h1 = x1 & 2u, h2 = x2 & 4u;
+                if ((dup >> L) & 7u) {  // cold: re-evaluate the three probes in serial order
+                    int c;
+                    uint32_t z;
+                    h0 = probe_cold(L, ins, h0, &c, &z);
+                    if (h0) {
+                        fcand = c;
+                        fnz = z;
+                    } else {
+                        h1 = probe_cold(L + 1, ins, h1, &c, &z);
+                        if (h1) {
+                            fcand = c;
+                            fnz = z;
+                        } else {
+                            h2 = probe_cold(L + 2, ins | 3u << L, h2, &c, &z);  // read after t and t+1 (:150)
+                            fcand = c;
+                            fnz = z;
+                        }
+                    }
+                }
+                if (h0) {
+                    ins |= 3u << L;
                     mps = t;
                 } else {
-                    ins |= 4u << L;  // :152 / :157
-                    if (r1.hit) {
-                        m = r1;
+                    ins |= 7u << L;  // :152 / :157
+                    if (h1) {
                         mps = t + 1;
-                    } else {
-                        m = probe(L + 2, E2);  // read after the inserts of t and t+1 (:150)
-                        if (!m.hit) {
-                            s = nextS;
-                            continue;
-                        }
+                    } else if (h2) {
                         mps = t + 2;
+                    } else {
+                        s = nextS;
+                        continue;
                     }
                 }
                 from_rematch = false;
             }
 
             // ---------------- a verified candidate at mps ----------------
-            if (!m.fw) {
-                const int L = mps - wbase;
-                m.cand = __shfl_sync(kFullMask, cand, L);
-                m.nz = __shfl_sync(kFullMask, nz, L);
-                m.bb = __shfl_sync(kFullMask, bb, L);
+            int mcand;
+            uint32_t mnz;
+            if (fcand >= 0) {
+                mcand = fcand;
+                mnz = fnz;
+            } else {
+                mcand = __shfl_sync(kFullMask, cand, mps - wbase);
+                mnz = __shfl_sync(kFullMask, nz, mps - wbase);
             }
-            const int f = m.nz ? __ffs(m.nz) - 1 : kSnapFwd;
+            const int mbb = mnz >> 24;
+            mnz &= 0xffffffu;
+            const int f = mnz ? __ffs(mnz) - 1 : kSnapFwd;
             int base = mps, known = f;
             if (!from_rematch && P::kBackExtend) {  // :169-172
-                const int room = min(m.cand, mps - nextEmit);
-                int back = min(m.bb, room);
-                if (back == 4 && room > 4) back += extend_backward(src, m.cand - 4, mps - 4, nextEmit, lane);
+                const int room = min(mcand, mps - nextEmit);
+                int back = min(mbb, room);
+                if (back == 4 && room > 4) back += extend_backward(src, mcand - 4, mps - 4, nextEmit, lane);
                 base = mps - back;
                 known = back + f;
             }
-            repeat = mps - m.cand;
+            repeat = mps - mcand;
             // Go: s = base + min match, then 8-byte chunks while s <= n-8 (:181-188)
-            int q_stop = base + P::kMinMatch;
-            if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
-            int e;
-            if (f < kSnapFwd) {
-                e = min(base + known, q_stop);
-            } else {
-                const int sc = base + P::kMinMatch + 8 * ((known - P::kMinMatch) >> 3);
-                e = min(extend_forward8(src, sc, sc - repeat, n - 8, lane), q_stop);
+            int e = base + known;
+            if (f == kSnapFwd || e > n - 8) {
+                int q_stop = base + P::kMinMatch;
+                if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
+                if (f == kSnapFwd) {
+                    const int sc = base + P::kMinMatch + 8 * ((known - P::kMinMatch) >> 3);
+                    e = extend_forward8(src, sc, sc - repeat, n - 8, lane);
+                }
+                e = min(e, q_stop);
             }
-            pe_kind = from_rematch ? 1 : 2;
-            pe_ne = nextEmit;
-            pe_base = base;
-            pe_repeat = repeat;
-            pe_end = e;
+            if (lane == q_cnt) {
+                q_kind = from_rematch ? 1 : 2;
+                q_ne = nextEmit;
+                q_base = base;
+                q_rep = repeat;
+                q_end = e;
+            }
+            q_cnt++;
             rep_snap = true;
-            Rnz = m.nz;
+            Rnz = mnz;
             Rps = mps;
             s = e;
             rematch = true;
         }
-        if (done) break;
 
         // ---------------- write back the inserts the replay performed ----------------
         if (((ins >> lane) & 1u) && (same & ins & above) == 0) {  // a later insert on the same slot wins
@@ -535,7 +573,6 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         __syncwarp();
     }
 
-    if (pe_kind && !flush_pending()) return 0;
     // emitRemainder (encode_l1.go:268-282)
     if (nextEmit < n) {
         if (d + n - nextEmit > dstLimit) return 0;
