@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -175,7 +176,8 @@ void release_tables(DeviceState &st, const TableWs &w) {
 }
 
 int launch_encode(int device, int level, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send,
-                  uint8_t *dst, const uint64_t *dbeg, uint32_t *out_len, cudaStream_t stream) {
+                  uint8_t *dst, const uint64_t *dbeg, uint32_t *out_len, cudaStream_t stream, const int *gate = nullptr,
+                  int slice = 0) {
     if (nblk == 0) return MZCU_OK;
     DeviceState &st = g_dev[device];
     int *counter = st.counters + (st.next_counter.fetch_add(1) % kCounterSlots);
@@ -189,16 +191,17 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
         int rc = acquire_tables(st, (size_t)grid * mz::kEncL1Warps * mz::kEncL1WsBytesPerWarp, &ws);
         if (rc) return rc;
         if (level == MZCU_LEVEL_FASTEST)
-            mz::encode_l1_kernel<false><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len,
-                                                                                  counter, static_cast<mz::Slot *>(ws.ptr));
+            mz::encode_l1_kernel<false><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(
+                nblk, src, sbeg, send, dst, dbeg, out_len, counter, static_cast<mz::Slot *>(ws.ptr), gate, slice);
         else
-            mz::encode_l1_kernel<true><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len,
-                                                                                 counter, static_cast<mz::Slot *>(ws.ptr));
+            mz::encode_l1_kernel<true><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(
+                nblk, src, sbeg, send, dst, dbeg, out_len, counter, static_cast<mz::Slot *>(ws.ptr), gate, slice);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaEventRecord(ws.done, stream);
         release_tables(st, ws);
         if (e != cudaSuccess) return fail(MZCU_ERR_CUDA, "encode_l1 launch: %s", cudaGetErrorString(e));
     } else if (level == MZCU_LEVEL_BALANCED) {
+        if (gate) return fail(MZCU_ERR_INVALID_ARG, "encode_l2 has no arrival gate");
         int grid = (nblk + mz::kEncL2Warps - 1) / mz::kEncL2Warps;
         int resident = st.num_sms * st.enc_l2_ctas_per_sm;
         if (grid > resident) grid = resident;
@@ -239,8 +242,26 @@ int launch_pack(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, 
     return MZCU_OK;
 }
 
-constexpr int kMaxChunks = 4;
-constexpr int kMinChunkBlocks = 256;  // do not split batches below this many blocks per chunk
+constexpr int kMaxChunks = 16;
+// chunks per host call; MZCU_CHUNKS overrides (tuning knob)
+int max_chunks() {
+    static const int v = [] {
+        int c = 8;
+        if (const char *e = getenv("MZCU_CHUNKS")) c = atoi(e);
+        return c < 1 ? 1 : c > kMaxChunks ? kMaxChunks : c;
+    }();
+    return v;
+}
+constexpr int kMinChunkBlocks = 256;
+// slice of the sliced source copy (0 disables); MZCU_SLICE_KB overrides (tuning knob)
+int slice_bytes() {
+    static const int v = [] {
+        int kb = 32;
+        if (const char *e = getenv("MZCU_SLICE_KB")) kb = atoi(e);
+        return kb <= 0 ? 0 : kb << 10;
+    }();
+    return v;
+}  // do not split batches below this many blocks per chunk
 
 // ---- pooled host-call workspaces ------------------------------------------
 struct Workspace {
@@ -254,7 +275,10 @@ struct Workspace {
     uint64_t *h_tab = nullptr;  // pinned mirror of d_tab
     cudaStream_t cs[kMaxChunks] = {};  // chunk pipelines (copy in / kernels / copy out overlap across chunks)
     cudaEvent_t tab_ready = nullptr;
+    int *d_arrived = nullptr;  // arrival gate of the sliced host->device source copy
+    int *h_slice_no = nullptr; // pinned 1, 2, 3, ... (source of the gate writes)
 };
+constexpr int kMaxSlices = 1024;
 
 std::mutex g_ws_mu;
 std::vector<Workspace *> g_ws_free;
@@ -277,6 +301,10 @@ int ws_acquire(int device, Workspace **out) {
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
     for (int c = 0; c < kMaxChunks && e == cudaSuccess; c++) e = cudaStreamCreateWithFlags(&w->cs[c], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->tab_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_arrived, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&w->h_slice_no, kMaxSlices * sizeof(int));
+    if (e == cudaSuccess)
+        for (int i = 0; i < kMaxSlices; i++) w->h_slice_no[i] = i + 1;
     if (e != cudaSuccess) {
         delete w;
         return fail(MZCU_ERR_CUDA, "workspace: %s", cudaGetErrorString(e));
@@ -514,12 +542,83 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
         h_dbeg[i] = dof;
         dof += (src_off[i + 1] - src_off[i] + 2 + 15) & ~size_t(15);
     }
+    // Sliced pipeline (LevelFastest / LevelSuperFast, equal-sized contiguous blocks): the
+    // walk of a block is a serial chain that eats ~10 MB/s, PCIe delivers ~50 GB/s, so
+    // instead of waiting for whole blocks the source goes up in SLICES -- bytes
+    // [k*S, (k+1)*S) of every block, one strided copy -- each followed by a 4-byte
+    // write of k+1 to the arrival gate, while ONE persistent encode launch already
+    // runs and chases the arrival front (gate_wait in mz_encode_l1.cuh).  The call
+    // then costs max(kernel, copy) instead of copy + kernel.
+    {
+        const size_t B = src_off[1] - src_off[0];
+        bool uniform = level != MZCU_LEVEL_BALANCED && nblk >= 64 && B >= (256u << 10) && B % 128 == 0 && slice_bytes() > 0;
+        for (int i = 1; uniform && i < nblk; i++) {
+            const size_t n = src_off[i + 1] - src_off[i];
+            uniform = i + 1 < nblk ? n == B : (n <= B && n > 0);
+        }
+        if (uniform) {
+            const size_t S = (size_t)slice_bytes();
+            const int nsl = (int)((B + S - 1) / S);
+            const size_t last = src_off[nblk] - src_off[nblk - 1];
+            const int full = last == B ? nblk : nblk - 1;  // rows of the strided copies
+            if (nsl <= kMaxSlices) {
+                cudaStream_t cp = w->cs[0];
+                CU_TRY(cudaMemsetAsync(w->d_arrived, 0, sizeof(int), w->stream));
+                CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 3 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
+                CU_TRY(cudaEventRecord(w->tab_ready, w->stream));
+                CU_TRY(cudaEventRecord(w->ev0, w->stream));
+                rc = launch_encode(device, level, nblk, w->d_src, d_sbeg, d_send, w->d_dst, d_dbeg, d_out, w->stream,
+                                   w->d_arrived, (int)S);
+                if (rc) return rc;
+                CU_TRY(cudaStreamWaitEvent(cp, w->tab_ready, 0));  // the gate is zeroed before the first write
+                cudaError_t ce = cudaSuccess;
+                for (int k = 0; k < nsl && ce == cudaSuccess; k++) {
+                    const size_t o = (size_t)k * S, wd = o + S <= B ? S : B - o;
+                    ce = cudaMemcpy2DAsync(w->d_src + o, B, src + base + o, B, wd, (size_t)full, cudaMemcpyHostToDevice, cp);
+                    if (ce == cudaSuccess && full < nblk && o < last)
+                        ce = cudaMemcpyAsync(w->d_src + (size_t)full * B + o, src + base + (size_t)full * B + o,
+                                             o + wd <= last ? wd : last - o, cudaMemcpyHostToDevice, cp);
+                    if (ce == cudaSuccess)
+                        ce = cudaMemcpyAsync(w->d_arrived, w->h_slice_no + k, sizeof(int), cudaMemcpyHostToDevice, cp);
+                }
+                if (ce != cudaSuccess) {
+                    // never leave the kernel waiting for slices that will not come
+                    cudaMemcpyAsync(w->d_arrived, w->h_slice_no + kMaxSlices - 1, sizeof(int), cudaMemcpyHostToDevice, cp);
+                    cudaStreamSynchronize(cp);
+                    cudaStreamSynchronize(w->stream);
+                    return fail(MZCU_ERR_CUDA, "sliced copy: %s", cudaGetErrorString(ce));
+                }
+                if (crc_out) {  // checksum of the uncompressed blocks, behind the encode = all resident (writer.go:672)
+                    rc = launch_crc(device, nblk, w->d_src, d_sbeg, d_send, d_crc, w->stream);
+                    if (rc == MZCU_OK)
+                        CU_TRY(cudaMemcpyAsync(crc_out, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                               w->stream));
+                }
+                if (rc == MZCU_OK) rc = launch_pack(device, nblk, w->d_dst, d_dbeg, d_out, w->d_src, d_poff, w->stream);
+                if (rc == MZCU_OK)
+                    CU_TRY(cudaMemcpyAsync(h_poff, d_poff, (size_t)(nblk + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                           w->stream));
+                CU_TRY(cudaStreamSynchronize(cp));
+                CU_TRY(cudaStreamSynchronize(w->stream));
+                if (rc) return rc;
+                const size_t packed = h_poff[nblk];
+                if (packed > dst_cap) return fail(MZCU_ERR_DST_TOO_SMALL, "packed output exceeds capacity %zu", dst_cap);
+                if (packed) CU_TRY(cudaMemcpyAsync(dst, w->d_src, packed, cudaMemcpyDeviceToHost, w->stream));
+                for (int i = 0; i <= nblk; i++) dst_off_out[i] = h_poff[i];
+                CU_TRY(cudaEventRecord(w->ev1, w->stream));
+                CU_TRY(cudaStreamSynchronize(w->stream));
+                cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
+                return MZCU_OK;
+            }
+        }
+    }
+
     // Chunk pipeline: the batch is cut into up to kMaxChunks runs of blocks, each on its
     // own stream (H2D -> crc -> encode -> pack -> D2H of the sizes).  The kernels are
     // latency bound per block, so chunks overlap on the device while later chunks are
     // still arriving over PCIe, and packed chunks leave while others still encode.
     int nchunks = nblk / kMinChunkBlocks;
-    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    if (nchunks > max_chunks()) nchunks = max_chunks();
     if (nchunks < 1) nchunks = 1;
     int first[kMaxChunks + 1];
     for (int c = 0; c <= nchunks; c++) first[c] = (int)((int64_t)nblk * c / nchunks);
@@ -616,7 +715,7 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
     // out run per chunk on their own streams.  Source ranges must be ascending for the
     // per-chunk H2D; otherwise the batch goes as one chunk.
     int nchunks = nblk / kMinChunkBlocks;
-    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    if (nchunks > max_chunks()) nchunks = max_chunks();
     if (nchunks < 1) nchunks = 1;
     bool ascending = true;
     for (int i = 0; i + 1 < nblk; i++)

@@ -39,9 +39,28 @@ namespace mz {
 // with the lanes comparing consecutive 8-byte words; the first round uses 4
 // lanes (most matches end within 32 bytes, and the candidate side is a random
 // DRAM sector), later rounds all 32.
-__device__ __noinline__ int extend_forward8(const uint8_t *src, int s, int cand, int limit, int lane) {
+// ---- arrival gate (host-pointer encode, mz_api.cu) ---------------------------
+// When the source is still arriving over PCIe the host copies it in slices
+// (bytes [k*slice, (k+1)*slice) of EVERY block, then a 4-byte write of k+1 to
+// *gate), and the kernel chases the arrival front: before reading source bytes
+// ahead of the cursor a warp waits until enough slices have landed.  gate ==
+// nullptr: everything is resident.  Returns the number of bytes of each block
+// that have arrived.
+__device__ __forceinline__ int gate_wait(const int *gate, int slice, int need) {
+    for (;;) {
+        int k;
+        asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(k) : "l"(gate) : "memory");
+        const long long have = (long long)k * slice;
+        if (have >= need) return have > 0x7fffffffll ? 0x7fffffff : (int)have;
+        __nanosleep(256);
+    }
+}
+
+__device__ __noinline__ int extend_forward8(const uint8_t *src, int s, int cand, int limit, int lane, const int *gate,
+                                            int slice) {
     int width = 4;
     for (;;) {
+        if (gate) gate_wait(gate, slice, min(s + 8 * width + 16, limit + 8));
         int pos = s + 8 * lane;
         const bool act = lane < width;
         bool past = pos > limit;
@@ -195,10 +214,17 @@ struct SrcRing {
     const uint8_t *src;
     int n;
     int filled;  // chunks up to here are loaded (positions >= n read as 0)
+    const int *gate;  // arrival gate (see gate_wait), nullptr when the source is resident
+    int slice;
+    int avail;  // bytes of this block known to have arrived
 
     // Loads 256-byte chunks until `want_end` is covered.  All lanes call.
     __device__ __forceinline__ void ensure(int want_end, int lane) {
         while (filled < want_end) {
+            if (gate) {
+                const int need = min(filled + kRingChunk + 16, n);
+                if (need > avail) avail = gate_wait(gate, slice, need);
+            }
             int pos = filled + 8 * lane;
             uint64_t v = 0;
             if (pos + 8 <= n) {
@@ -263,7 +289,7 @@ __device__ __forceinline__ uint32_t nzmask24(const uint32_t *x, const uint32_t *
 // table then holds that insert, whose bytes are still in the ring.  Returns
 // nzmask24(src[cand..], src[pos..]) | back-equal byte count (<= 4) << 24.
 __device__ __noinline__ uint32_t probe_forwarded(const uint32_t *ring_mem, int pos, int cand) {
-    SrcRing ring{const_cast<uint32_t *>(ring_mem), nullptr, 0, 0};
+    SrcRing ring{const_cast<uint32_t *>(ring_mem), nullptr, 0, 0, nullptr, 0, 0};
     uint32_t A[7], B[7];
     ring.fetch28(pos - 4, A);
     ring.fetch28(cand - 4, B);
@@ -291,13 +317,13 @@ __device__ __noinline__ uint32_t probe_forwarded(const uint32_t *ring_mem, int p
 // the result (0 = incompressible) is the same.
 template <class P>
 __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Slot *table, uint32_t *ring_mem,
-                               const int lane) {
+                               const int lane, const int *gate, const int slice) {
     const int sLimit = n - kInputMargin;
     const int dstLimit = P::dst_limit(n);
     const int fill_limit = (n + 64 + kRingChunk - 1) & ~(kRingChunk - 1);
     constexpr uint32_t kMinMask = P::kMinMatch == 8 ? 0xffu : 0xfu;
 
-    SrcRing ring{ring_mem, src, n, 0};
+    SrcRing ring{ring_mem, src, n, 0, gate, slice, 0};
     ring.ensure(min(2 * kRingChunk, fill_limit), lane);
 
     // Empty slots read as candidate 0 (encode_l1.go:52,86): position 0 and its bytes.
@@ -464,7 +490,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                     ins |= 3u << L;
                     int base = t + 1;
                     base -= extend_backward(src, base - repeat, base, nextEmit, lane);
-                    s = extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane);
+                    s = extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane, gate, slice);
                     if (lane == q_cnt) {
                         q_kind = 3;
                         q_ne = nextEmit;
@@ -547,7 +573,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                 if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
                 if (f == kSnapFwd) {
                     const int sc = base + P::kMinMatch + 8 * ((known - P::kMinMatch) >> 3);
-                    e = extend_forward8(src, sc, sc - repeat, n - 8, lane);
+                    e = extend_forward8(src, sc, sc - repeat, n - 8, lane, gate, slice);
                 }
                 e = min(e, q_stop);
             }
@@ -587,7 +613,7 @@ template <bool kSuperFast>
 __global__ void __launch_bounds__(kEncL1Warps * 32, MZ_ENC_L1_MIN_CTAS)
 encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
-                 uint32_t *__restrict__ out_len, int *counter, Slot *tables) {
+                 uint32_t *__restrict__ out_len, int *counter, Slot *tables, const int *gate, int slice) {
     __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -605,11 +631,11 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
         if (n64 >= kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {
             const int n = (int)n64;
             if (kSuperFast)
-                res = n <= 65536 ? encode_l1_block<L0Params<true>>(dp, sp, n, table, rings[warp], lane)
-                                 : encode_l1_block<L0Params<false>>(dp, sp, n, table, rings[warp], lane);
+                res = n <= 65536 ? encode_l1_block<L0Params<true>>(dp, sp, n, table, rings[warp], lane, gate, slice)
+                                 : encode_l1_block<L0Params<false>>(dp, sp, n, table, rings[warp], lane, gate, slice);
             else
-                res = n <= 65536 ? encode_l1_block<L1Params<true>>(dp, sp, n, table, rings[warp], lane)
-                                 : encode_l1_block<L1Params<false>>(dp, sp, n, table, rings[warp], lane);
+                res = n <= 65536 ? encode_l1_block<L1Params<true>>(dp, sp, n, table, rings[warp], lane, gate, slice)
+                                 : encode_l1_block<L1Params<false>>(dp, sp, n, table, rings[warp], lane, gate, slice);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();

@@ -314,6 +314,29 @@ def test_encode_packed_host_api(oracle):
     assert not status.any() and out.tobytes() == b"".join(raws[i] for i in keep)
 
 
+@pytest.mark.parametrize("level", [-1, 1])
+@pytest.mark.parametrize("last", [256 << 10, 100001])
+def test_encode_packed_sliced_source(oracle, level, last):
+    """Equal-sized contiguous blocks take the sliced host->device pipeline (the
+    kernel starts before the source has arrived and chases the arrival front);
+    the bytes must not depend on it.  The last block may be short."""
+    import synth
+    B, nblk = 256 << 10, 80
+    body = synth.make_blocks("json", nblk - 1, B, seed=7).cpu().numpy().reshape(-1)
+    tail = synth.make_blocks("log", 1, B, seed=8).cpu().numpy().reshape(-1)[:last]
+    src = np.ascontiguousarray(np.concatenate([body, tail]))
+    soff = np.array([i * B for i in range(nblk)] + [(nblk - 1) * B + last], dtype=np.uint64)
+    dst = np.zeros(len(src), dtype=np.uint8)
+    poff = np.zeros(nblk + 1, dtype=np.uint64)
+    total = mz.encode_blocks_packed_into(src, soff, dst, poff, level)
+    assert total == int(poff[-1]) and 0 < total < len(src)
+    for i in list(range(0, nblk, 9)) + [nblk - 2, nblk - 1]:
+        data = src[int(soff[i]):int(soff[i + 1])].tobytes()
+        assert dst[int(poff[i]):int(poff[i + 1])].tobytes() == oracle.encode_block(data, level), i
+    out, status = mz.decode_blocks(dst[:total], poff, soff)
+    assert not status.any() and np.array_equal(out, src)
+
+
 def test_concurrent_callers(oracle):
     """The seam must tolerate concurrent calls from arbitrary threads
     (writer.go:670 spawns one goroutine per block; SURVEY 8b threading row)."""
