@@ -344,10 +344,11 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
     bool rematch = false;  // the cursor is in the re-match loop (:222-265)
     bool done = false;     // reached emitRemainder
 
-    // queue of this batch's matches, entry i in lane i:
-    // kind 1 copy, 2 literals [ne, base) + copy, 3 literals + repeat
-    int q_kind = 0, q_ne = 0, q_base = 0, q_rep = 0, q_end = 0;
+    // queue of this batch's matches, entry i in lane i: [base, end) at offset rep
+    // (the literals of an entry start where the previous entry ended: emitted)
+    int q_base = 0, q_rep = 0, q_end = 0;  // q_rep = offset | kind << 24
     int q_cnt = 0;
+    int emitted = 0;  // nextEmit as the token writer sees it
 
     const unsigned below = (1u << lane) - 1u;
     const unsigned above = ~((2u << lane) - 1u);
@@ -376,19 +377,20 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
 
         // ---------------- the loads are in flight: write the queued tokens ----------------
         for (int i = 0; i < q_cnt; i++) {
-            const int kind = __shfl_sync(kFullMask, q_kind, i);
-            const int ne = __shfl_sync(kFullMask, q_ne, i);
             const int base = __shfl_sync(kFullMask, q_base, i);
-            const int rep = __shfl_sync(kFullMask, q_rep, i);
+            const int rk = __shfl_sync(kFullMask, q_rep, i);
             const int end = __shfl_sync(kFullMask, q_end, i);
+            const int kind = rk >> 24, rep = rk & 0xffffff;  // kind 3: literals + repeat, 0: (literals +) copy
+            const int ne = emitted;
+            emitted = end;
             const int length = end - base;
-            if (kind == 3) {  // :94-145
+            if (kind) {  // :94-145
                 if (d + (base - ne) > dstLimit) return 0;
                 d += emit_literal(dst + d, src + ne, base - ne, lane);
                 d += emit_repeat(dst + d, length, lane);
                 continue;
             }
-            if (kind == 2 && ne != base) {  // :190-206
+            if (ne != base) {  // :190-206
                 if (base - ne > P::kMaxFuseLits || rep < kMinCopy2Offset) {
                     if (d + (end - ne) > dstLimit) return 0;
                     d += emit_literal(dst + d, src + ne, base - ne, lane);
@@ -431,8 +433,8 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         const unsigned Brep = __ballot_sync(kFullMask, rep_lane && rep4 == W[1]);
 
         // ---------------- replay the serial walk over the window ----------------
-        unsigned ins = 0;       // lanes whose position was inserted; serial order = lane order
-        bool rep_snap = false;  // repeat checks come from the last match's snapshot (Rnz, Rps)
+        unsigned ins = 0;     // lanes whose position was inserted; serial order = lane order
+        int rep_snap = 0;     // repeat checks come from the last match's snapshot (Rnz, Rps)
         uint32_t Rnz = 0;
         int Rps = 0;
 
@@ -447,110 +449,146 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             *fnz = probe_forwarded(ring_mem, wbase + L, *fcand);
             return (*fnz & kMinMask) == 0;
         };
+        // End of a match that starts at `base`, is known equal for `known` bytes and whose
+        // snapshot comparison found `f` equal bytes from the probe (24 = all of them).
+        // Go: s = base + min match, then 8-byte chunks while s <= n-8 (:181-188)
+        auto match_end = [&](int base, int known, int f, int offset) -> int {
+            int e = base + known;
+            if (f == kSnapFwd || e > n - 8) {
+                int q_stop = base + P::kMinMatch;
+                if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
+                if (f == kSnapFwd) {
+                    const int sc = base + P::kMinMatch + 8 * ((known - P::kMinMatch) >> 3);
+                    e = extend_forward8(src, sc, sc - offset, n - 8, lane, gate, slice);
+                }
+                e = min(e, q_stop);
+            }
+            return e;
+        };
 
         for (;;) {
-            const int L = s - wbase;
-            int mps, fcand = -1;  // position of the verified probe; its forwarded candidate if any
-            uint32_t fnz = 0;
-            bool from_rematch;
             if (rematch) {
-                nextEmit = s;
-                if (s >= sLimit) {
-                    done = true;
-                    break;
-                }
-                if (L >= K) break;
-                bool hit = (E0 >> L) & 1u;  // read before this step's inserts (:236-239)
-                if ((dup >> L) & 1u) hit = probe_cold(L, ins, hit, &fcand, &fnz);
-                ins |= 5u << (L - 2);
-                if (!hit) {
-                    rematch = false;
-                    s++;
-                    continue;
-                }
-                mps = s;
-                from_rematch = true;
-            } else {
-                const int t = s;
-                const int nextS = t + ((t - nextEmit) >> P::kSkipLog) + P::kStep;  // :79
-                if (nextS > sLimit) {
-                    done = true;
-                    break;
-                }
-                if (L + 2 >= K) break;
-                bool rhit;  // repeat check at t+1 (:94)
-                if (rep_snap) {
-                    const int dl = t + 1 - Rps;
-                    if (dl > kSnapFwd - 4) break;  // not covered by the snapshot: next batch
-                    rhit = ((Rnz >> dl) & 0xfu) == 0;
-                } else {
-                    rhit = (Brep >> (L + 1)) & 1u;
-                }
-                if (rhit) {
-                    ins |= 3u << L;
-                    int base = t + 1;
-                    base -= extend_backward(src, base - repeat, base, nextEmit, lane);
-                    s = extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane, gate, slice);
-                    if (lane == q_cnt) {
-                        q_kind = 3;
-                        q_ne = nextEmit;
-                        q_base = base;
-                        q_rep = repeat;
-                        q_end = s;
-                    }
-                    q_cnt++;
+                // ---- the re-match chain (:222-265): back-to-back copies, no literals ----
+                for (;;) {
                     nextEmit = s;
                     if (s >= sLimit) {
                         done = true;
                         break;
                     }
-                    continue;
+                    const int L = s - wbase;
+                    if (L >= K) break;
+                    int fcand = -1;
+                    uint32_t fnz = 0;
+                    bool hit = (E0 >> L) & 1u;  // read before this step's inserts (:236-239)
+                    if ((dup >> L) & 1u) hit = probe_cold(L, ins, hit, &fcand, &fnz);
+                    ins |= 5u << (L - 2);
+                    if (!hit) {
+                        rematch = false;
+                        s++;
+                        break;
+                    }
+                    int mcand = fcand;
+                    uint32_t mnz = fnz;
+                    if (fcand < 0) {
+                        mcand = __shfl_sync(kFullMask, cand, L);
+                        mnz = __shfl_sync(kFullMask, nz, L);
+                    }
+                    mnz &= 0xffffffu;
+                    const int f = mnz ? __ffs(mnz) - 1 : kSnapFwd;
+                    repeat = s - mcand;
+                    const int e = match_end(s, f, f, repeat);
+                    if (lane == q_cnt) {
+                        q_base = s;
+                        q_rep = repeat;
+                        q_end = e;
+                    }
+                    q_cnt++;
+                    rep_snap = 1;
+                    Rnz = mnz;
+                    Rps = s;
+                    s = e;
                 }
-                const unsigned x0 = E0 >> L, x1 = E1 >> L, x2 = E2 >> L;
-                bool h0 = x0 & 1u, h1 = x1 & 2u, h2 = x2 & 4u;
-                if ((dup >> L) & 7u) {  // cold: re-evaluate the three probes in serial order
-                    int c;
-                    uint32_t z;
-                    h0 = probe_cold(L, ins, h0, &c, &z);
-                    if (h0) {
+                if (rematch) break;  // the chain left the window or reached the end
+            }
+
+            // ---- one search step at t (:70-160) ----
+            const int t = s;
+            const int L = t - wbase;
+            const int nextS = t + ((t - nextEmit) >> P::kSkipLog) + P::kStep;  // :79
+            if (nextS > sLimit) {
+                done = true;
+                break;
+            }
+            if (L + 2 >= K) break;
+            bool rhit;  // repeat check at t+1 (:94)
+            if (rep_snap) {
+                const int dl = t + 1 - Rps;
+                if (dl > kSnapFwd - 4) break;  // not covered by the snapshot: next batch
+                rhit = ((Rnz >> dl) & 0xfu) == 0;
+            } else {
+                rhit = (Brep >> (L + 1)) & 1u;
+            }
+            if (rhit) {
+                ins |= 3u << L;
+                int base = t + 1;
+                base -= extend_backward(src, base - repeat, base, nextEmit, lane);
+                s = extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane, gate, slice);
+                if (lane == q_cnt) {
+                    q_base = base;
+                    q_rep = repeat | 3 << 24;
+                    q_end = s;
+                }
+                q_cnt++;
+                nextEmit = s;
+                if (s >= sLimit) {
+                    done = true;
+                    break;
+                }
+                continue;
+            }
+            const unsigned x0 = E0 >> L, x1 = E1 >> L, x2 = E2 >> L;
+            bool h0 = x0 & 1u, h1 = x1 & 2u, h2 = x2 & 4u;
+            int fcand = -1;
+            uint32_t fnz = 0;
+            if ((dup >> L) & 7u) {  // cold: re-evaluate the three probes in serial order
+                int c;
+                uint32_t z;
+                h0 = probe_cold(L, ins, h0, &c, &z);
+                if (h0) {
+                    fcand = c;
+                    fnz = z;
+                } else {
+                    h1 = probe_cold(L + 1, ins, h1, &c, &z);
+                    if (h1) {
                         fcand = c;
                         fnz = z;
                     } else {
-                        h1 = probe_cold(L + 1, ins, h1, &c, &z);
-                        if (h1) {
-                            fcand = c;
-                            fnz = z;
-                        } else {
-                            h2 = probe_cold(L + 2, ins | 3u << L, h2, &c, &z);  // read after t and t+1 (:150)
-                            fcand = c;
-                            fnz = z;
-                        }
+                        h2 = probe_cold(L + 2, ins | 3u << L, h2, &c, &z);  // read after t and t+1 (:150)
+                        fcand = c;
+                        fnz = z;
                     }
                 }
-                if (h0) {
-                    ins |= 3u << L;
-                    mps = t;
+            }
+            int mps;  // position of the verified probe
+            if (h0) {
+                ins |= 3u << L;
+                mps = t;
+            } else {
+                ins |= 7u << L;  // :152 / :157
+                if (h1) {
+                    mps = t + 1;
+                } else if (h2) {
+                    mps = t + 2;
                 } else {
-                    ins |= 7u << L;  // :152 / :157
-                    if (h1) {
-                        mps = t + 1;
-                    } else if (h2) {
-                        mps = t + 2;
-                    } else {
-                        s = nextS;
-                        continue;
-                    }
+                    s = nextS;
+                    continue;
                 }
-                from_rematch = false;
             }
 
-            // ---------------- a verified candidate at mps ----------------
-            int mcand;
-            uint32_t mnz;
-            if (fcand >= 0) {
-                mcand = fcand;
-                mnz = fnz;
-            } else {
+            // ---- a verified candidate at mps: literals + copy ----
+            int mcand = fcand;
+            uint32_t mnz = fnz;
+            if (fcand < 0) {
                 mcand = __shfl_sync(kFullMask, cand, mps - wbase);
                 mnz = __shfl_sync(kFullMask, nz, mps - wbase);
             }
@@ -558,7 +596,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             mnz &= 0xffffffu;
             const int f = mnz ? __ffs(mnz) - 1 : kSnapFwd;
             int base = mps, known = f;
-            if (!from_rematch && P::kBackExtend) {  // :169-172
+            if (P::kBackExtend) {  // :169-172
                 const int room = min(mcand, mps - nextEmit);
                 int back = min(mbb, room);
                 if (back == 4 && room > 4) back += extend_backward(src, mcand - 4, mps - 4, nextEmit, lane);
@@ -566,26 +604,14 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                 known = back + f;
             }
             repeat = mps - mcand;
-            // Go: s = base + min match, then 8-byte chunks while s <= n-8 (:181-188)
-            int e = base + known;
-            if (f == kSnapFwd || e > n - 8) {
-                int q_stop = base + P::kMinMatch;
-                if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
-                if (f == kSnapFwd) {
-                    const int sc = base + P::kMinMatch + 8 * ((known - P::kMinMatch) >> 3);
-                    e = extend_forward8(src, sc, sc - repeat, n - 8, lane, gate, slice);
-                }
-                e = min(e, q_stop);
-            }
+            const int e = match_end(base, known, f, repeat);
             if (lane == q_cnt) {
-                q_kind = from_rematch ? 1 : 2;
-                q_ne = nextEmit;
                 q_base = base;
                 q_rep = repeat;
                 q_end = e;
             }
             q_cnt++;
-            rep_snap = true;
+            rep_snap = 1;
             Rnz = mnz;
             Rps = mps;
             s = e;

@@ -343,15 +343,25 @@ static int64_t encode_l1(uint8_t *dst, const uint8_t *src, int n, int tableBits,
         }
 
         /* extend backwards, :169-172 */
+#ifdef MZO_STATS
+        int probe_pos = s;
+#endif
         while (candidate > 0 && s > nextEmit && src[candidate - 1] == src[s - 1]) {
             candidate--;
             s--;
         }
+#ifdef MZO_STATS
+        if (probe_pos - s > 4) STAT(8); /* backward extension beyond a 4-byte snapshot */
+#endif
         int base = s;
         repeat = base - candidate; /* :176 */
         s += 4;
         candidate += 4;
         s = extend8(src, s, candidate, n - 8); /* :181-188 */
+#ifdef MZO_STATS
+        if (s - probe_pos >= 24) STAT(9); /* forward match beyond a 24-byte snapshot */
+        mzo_stats[12] += (uint64_t)(s - base);
+#endif
         int length = s - base;
         if (nextEmit != base) { /* :190-206 */
             if (base - nextEmit > maxFuseLits || repeat < kMinCopy2Offset) {
@@ -397,6 +407,10 @@ static int64_t encode_l1(uint8_t *dst, const uint8_t *src, int n, int tableBits,
             s += 4;
             candidate += 4;
             s = extend8(src, s, candidate, n - 8);
+#ifdef MZO_STATS
+            if (s - base >= 24) STAT(10);
+            mzo_stats[13] += (uint64_t)(s - base);
+#endif
             d += mzo_emit_copy(dst + d, repeat, s - base);
         }
     }
