@@ -33,7 +33,8 @@ def lib():
         u8p, u64p, u32p, i32p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
         L.mzo_max_encoded_len.restype = C.c_int64
         L.mzo_max_encoded_len.argtypes = [C.c_int64]
-        for f in (L.mzo_encode_block_l0, L.mzo_encode_block_l1, L.mzo_encode_block_l2):
+        for f in (L.mzo_encode_block_l0, L.mzo_encode_block_l1, L.mzo_encode_block_l2,
+                  L.mzo_encode_block_l0_asm, L.mzo_encode_block_l1_asm):
             f.restype = C.c_int64
             f.argtypes = [u8p, u8p, C.c_size_t]
         L.mzo_decode_block.restype = C.c_int
@@ -80,11 +81,15 @@ def max_encoded_len(n):
     return int(lib().mzo_max_encoded_len(n))
 
 
-def encode_block(src, level):
-    """encodeBlock / encodeBlockBetter: token stream without header; b'' = 0 (incompressible)."""
+def encode_block(src, level, flavor="go"):
+    """encodeBlock / encodeBlockBetter: token stream without header; b'' = 0 (incompressible).
+    flavor "go" = the pure-Go functions (noasm build), "asm" = the amd64 assembly flavour."""
     s = _in(src)
     dst = np.empty(s.size + 64, dtype=np.uint8)
-    f = {-1: lib().mzo_encode_block_l0, 1: lib().mzo_encode_block_l1, 2: lib().mzo_encode_block_l2}[level]
+    if flavor == "asm":
+        f = {-1: lib().mzo_encode_block_l0_asm, 1: lib().mzo_encode_block_l1_asm}[level]
+    else:
+        f = {-1: lib().mzo_encode_block_l0, 1: lib().mzo_encode_block_l1, 2: lib().mzo_encode_block_l2}[level]
     n = f(dst.ctypes.data, _ptr(s), s.size)
     return dst[:n].tobytes()
 

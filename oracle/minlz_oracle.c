@@ -567,6 +567,241 @@ int64_t mzo_encode_block_l0(uint8_t *dst, const uint8_t *src, size_t n) {
     return encode_l0(dst, src, nn, 13, 5, 5, nn - (nn >> 3) - 6, kMaxCopy3Lits);
 }
 
+/* ---- L1 / L0, AMD64-assembly flavour ------------------------------------
+ * What `go build` runs on amd64: the functions generated by
+ * _generate/gen.go:257-1155 genEncodeBlockAsm(name, tableBits, skipLog,
+ * hashBytes, maxLen) under fastOpts (gen.go:57-76), selected per block length by
+ * encode_amd64.go:37-189.  Same walk as the Go functions above; what differs
+ * (README.md:375 "will often produce slightly different output"):
+ *   sLimit = len-17 and the search ends on nextS >= sLimit      gen.go:52-53,369,459
+ *   dstLimit = len - len>>minSizeLog - 17; every bail test is
+ *     `dst [+ lits + literalMaxOverhead] >= dstLimit`             gen.go:380-417
+ *   matches and repeats extend with matchLen to the END of src   gen.go:632-654,859-887
+ *   table bits / skipLog / hash bytes / step per size class      gen.go:57-76
+ *   8 MiB variant clamps far candidates to s-2162685 (CMOV)      gen.go:466-490
+ *   Fast (L0): 8-byte compares, no literal fusing, no back-extension.
+ * PINNED: tests/test_ref_asm.py runs the reference's real assembly
+ * (oracle/_ref, see ref_shim.c) and requires byte identity on every corpus. */
+typedef struct {
+    int tableBits, skipLog, hashBytes, maxLen;
+    int match8, fuselits, checkBack, incLoop, minSizeLog;
+} asm_opts;
+
+static inline uint32_t hashNx(uint64_t u, int h, int nbytes) { /* gen.go:2072-2128 */
+    switch (nbytes) {
+    case 4: return (uint32_t)(((u << 32) * 2654435761ull) >> (64 - h));
+    case 5: return hash5(u, h);
+    case 6: return hash6(u, h);
+    case 7: return hash7(u, h);
+    default: return hash8(u, h);
+    }
+}
+
+/* gen.go:3190-3288 matchLen: exact common prefix of src[a..] and src[b..], at most `left` bytes */
+static inline int match_len_full(const uint8_t *src, int a, int b, int left) {
+    int n = 0;
+    while (left - n >= 8) {
+        uint64_t diff = ld64(src, a + n) ^ ld64(src, b + n);
+        if (diff) return n + (__builtin_ctzll(diff) >> 3);
+        n += 8;
+    }
+    while (n < left && src[a + n] == src[b + n]) n++;
+    return n;
+}
+
+/* gen.go:2161-2230 inline emitLiteral.  Reference quirk kept for parity: when
+ * maxLen is exactly 64 KiB the generator omits the `n < 1<<16` compare
+ * (gen.go:2193-2198, `maxLen >= 30+1<<16` is false) but still emits the
+ * four-byte form (gen.go:2200, `maxLen >= 1<<16`), so the 64K variants write
+ * literal runs of 286+ bytes with a 3-byte length (valid, not canonical). */
+static int emit_literal_asm(uint8_t *dst, const uint8_t *lit, size_t len, int maxLen) {
+    if (maxLen >= (1 << 16) && maxLen < 30 + (1 << 16) && len >= 1 + 29 + 256) {
+        uint32_t v = (uint32_t)len - 30;
+        dst[0] = 31 << 3 | TAG_LITERAL;
+        dst[1] = (uint8_t)v;
+        dst[2] = (uint8_t)(v >> 8);
+        dst[3] = (uint8_t)(v >> 16);
+        memcpy(dst + 4, lit, len);
+        return 4 + (int)len;
+    }
+    return mzo_emit_literal(dst, lit, len);
+}
+
+static int64_t encode_fast_asm(uint8_t *dst, const uint8_t *src, int n, const asm_opts *o) {
+    const int tb = o->tableBits, hb = o->hashBytes;
+    const int maxOffset = o->maxLen - 1;                         /* gen.go:291 */
+    const int clampFar = maxOffset > kMaxCopy3Offset;            /* gen.go:466,472 */
+    const int litOverhead = o->maxLen < 30 ? 1 : o->maxLen < 256 ? 2 : o->maxLen < 65536 ? 3 : 4; /* gen.go:1157-1169 */
+    const int mlen = o->match8 ? 8 : 4;
+    uint32_t *table = (uint32_t *)calloc((size_t)1 << tb, sizeof(uint32_t)); /* zero_loop, gen.go:337-353 */
+    if (!table) return 0;
+    const int sLimit = n - 17;                                   /* gen.go:369 */
+    const int64_t dstLimit = (int64_t)(n - 17) - (n >> o->minSizeLog); /* gen.go:380-391 */
+    int nextEmit = 0, s = 1, repeat = 1;
+    int64_t d = 0;
+    int candidate, base, length, offset;
+    uint64_t cv;
+#define BAIL_LITS(l) do { if (d + (l) + litOverhead >= dstLimit) { free(table); return 0; } } while (0) /* gen.go:395-417 */
+#define BAIL() do { if (d >= dstLimit) { free(table); return 0; } } while (0)
+#define CLAMP(c, minPos) do { if (clampFar && (c) <= (minPos)) (c) = (minPos); } while (0)        /* gen.go:477-482 */
+#define CVEQ(pos, v) (o->match8 ? ld64(src, (pos)) == (v) : ld32(src, (pos)) == (uint32_t)(v))
+
+search_loop:
+    {
+        int nextS = s + ((s - nextEmit) >> o->skipLog) + o->incLoop;        /* gen.go:449-455 */
+        if ((uint32_t)nextS >= (uint32_t)sLimit) goto emit_remainder;      /* gen.go:458-461 */
+        cv = ld64(src, s);
+        int minPos = s - kMaxCopy3Offset + 2;                             /* gen.go:467-469 */
+        uint32_t hash0 = hashNx(cv, tb, hb);
+        uint32_t hash1 = hashNx(hb > 7 ? ld64(src, s + 1) : cv >> 8, tb, hb);
+        candidate = (int)table[hash0];
+        int candidate2 = (int)table[hash1];
+        table[hash0] = (uint32_t)s;
+        table[hash1] = (uint32_t)(s + 1);
+        uint32_t hash2 = hashNx(hb > 6 ? ld64(src, s + 2) : cv >> 16, tb, hb);
+
+        if ((uint32_t)(cv >> 8) == ld32(src, s - repeat + 1)) {            /* gen.go:566-583 */
+            base = s + 1;
+            if (o->checkBack) {                                            /* gen.go:593-612 */
+                int i = base - repeat;
+                while (i != 0 && base > nextEmit && src[i - 1] == src[base - 1]) {
+                    base--;
+                    i--;
+                }
+            }
+            int litLen = base - nextEmit;
+            BAIL_LITS(litLen);                                             /* gen.go:619 */
+            d += emit_literal_asm(dst + d, src + nextEmit, (size_t)litLen, o->maxLen);
+            s += 5;                                                        /* gen.go:631 */
+            s += match_len_full(src, s, s - repeat, n - s);                /* gen.go:634-660 */
+            d += mzo_emit_repeat(dst + d, s - base);
+            nextEmit = s;
+            goto search_loop;                                              /* gen.go:688 */
+        }
+        /* no_repeat_found, gen.go:690-798 */
+        CLAMP(candidate, minPos);
+        if (CVEQ(candidate, cv)) goto candidate_match;
+        cv = hb > 7 ? ld64(src, s + 1) : cv >> 8;
+        candidate = (int)table[hash2];
+        CLAMP(candidate2, minPos);
+        if (CVEQ(candidate2, cv)) {
+            table[hash2] = (uint32_t)(s + 2);
+            s++;
+            candidate = candidate2;
+            goto candidate_match;
+        }
+        table[hash2] = (uint32_t)(s + 2);
+        cv = hb > 6 ? ld64(src, s + 2) : cv >> 8;
+        CLAMP(candidate, minPos);
+        if (CVEQ(candidate, cv)) {
+            s += 2;
+            goto candidate_match;
+        }
+        s = nextS;
+        goto search_loop;
+    }
+
+candidate_match:
+    if (o->checkBack)                                                      /* gen.go:803-824 */
+        while (candidate != 0 && s > nextEmit && src[candidate - 1] == src[s - 1]) {
+            s--;
+            candidate--;
+        }
+    BAIL();                                                                /* gen.go:828 */
+    base = s;
+    repeat = s - candidate;
+    s += mlen;
+    candidate += mlen;
+    length = match_len_full(src, s, candidate, n - s);                     /* gen.go:853-887 */
+    s += length;
+    length += mlen;
+    offset = repeat;
+    {
+        int litLen = base - nextEmit, ne = nextEmit;
+        nextEmit = s;
+        if (litLen == 0) goto emit_copy;
+        if (o->fuselits && litLen <= 3 && offset >= 64) {                  /* gen.go:907-943 */
+            if (maxOffset > kMaxCopy2Offset && offset > kMaxCopy2Offset)
+                d += mzo_emit_copy_lits3(dst + d, src + ne, litLen, offset, length);
+            else
+                d += mzo_emit_copy_lits2(dst + d, src + ne, litLen, offset, length);
+            goto copy_done;
+        }
+        BAIL_LITS(litLen);                                                 /* gen.go:945 */
+        d += emit_literal_asm(dst + d, src + ne, (size_t)litLen, o->maxLen);
+    }
+emit_copy:
+    d += mzo_emit_copy(dst + d, offset, length);                           /* gen.go:951 */
+copy_done:
+    if ((uint32_t)s >= (uint32_t)sLimit) goto emit_remainder;              /* gen.go:955-958 */
+    BAIL();                                                                /* gen.go:962-975 */
+    {   /* immediate re-match, gen.go:977-1090 */
+        uint64_t x = ld64(src, s - 2);
+        uint32_t h0 = hashNx(x, tb, hb);
+        cv = (hb > 6 || o->match8) ? ld64(src, s) : x >> 16;
+        uint32_t h1 = hashNx(cv, tb, hb);
+        candidate = (int)table[h1];
+        table[h0] = (uint32_t)(s - 2);
+        table[h1] = (uint32_t)s;
+        base = s;
+        s++;
+        if (clampFar && candidate <= base - kMaxCopy3Offset) goto search_loop; /* gen.go:1007-1021 */
+        if (!CVEQ(candidate, cv)) goto search_loop;
+        repeat = base - candidate;
+        BAIL();                                                            /* gen.go:1039 */
+        s += mlen - 1;
+        candidate += mlen;
+        length = match_len_full(src, s, candidate, n - s);
+        s += length;
+        length += mlen;
+        nextEmit = s;
+        offset = repeat;
+        goto emit_copy;
+    }
+
+emit_remainder:                                                            /* gen.go:1092-1119 */
+    free(table);
+    if (n - nextEmit != 0) {
+        if (d + (n - nextEmit) + litOverhead >= dstLimit) return 0;
+        d += emit_literal_asm(dst + d, src + nextEmit, (size_t)(n - nextEmit), o->maxLen);
+    }
+    return d;
+#undef BAIL_LITS
+#undef BAIL
+#undef CLAMP
+#undef CVEQ
+}
+
+/* encode_amd64.go:119-189 encodeBlock -> variants of gen.go:57-66 */
+int64_t mzo_encode_block_l1_asm(uint8_t *dst, const uint8_t *src, size_t n) {
+    if (n > MZO_MAX_BLOCK_SIZE) return 0;
+    asm_opts o = {15, 6, 6, 8 << 20, 0, 1, 1, 4, 5};
+    if (n > (2u << 20)) { /* encodeBlockAsm */ }
+    else if (n > (512u << 10)) o.maxLen = 2 << 20;
+    else if (n > (64u << 10)) { o.tableBits = 14; o.maxLen = 512 << 10; }
+    else if (n > (16u << 10)) { o.tableBits = 13; o.skipLog = 5; o.maxLen = 64 << 10; o.incLoop = 3; }
+    else if (n > (4u << 10)) { o.tableBits = 12; o.skipLog = 5; o.hashBytes = 5; o.maxLen = 16 << 10; o.incLoop = 3; }
+    else if (n > (1u << 10)) { o.tableBits = 10; o.skipLog = 5; o.hashBytes = 4; o.maxLen = 4 << 10; o.incLoop = 3; }
+    else if (n > kMinNonLiteralBlockSize) { o.tableBits = 9; o.skipLog = 4; o.hashBytes = 4; o.maxLen = 1 << 10; o.incLoop = 3; }
+    else return 0;
+    return encode_fast_asm(dst, src, (int)n, &o);
+}
+
+/* encode_amd64.go:37-107 encodeBlockFast -> variants of gen.go:68-76 */
+int64_t mzo_encode_block_l0_asm(uint8_t *dst, const uint8_t *src, size_t n) {
+    if (n > MZO_MAX_BLOCK_SIZE) return 0;
+    asm_opts o = {14, 5, 8, 8 << 20, 1, 0, 0, 4, 3};
+    if (n > (2u << 20)) { /* encodeFastBlockAsm */ }
+    else if (n > (512u << 10)) { o.tableBits = 13; o.maxLen = 2 << 20; }
+    else if (n > (64u << 10)) { o.tableBits = 13; o.maxLen = 512 << 10; }
+    else if (n > (16u << 10)) { o.tableBits = 12; o.skipLog = 4; o.maxLen = 64 << 10; }
+    else if (n > (4u << 10)) { o.tableBits = 11; o.skipLog = 4; o.maxLen = 16 << 10; }
+    else if (n > (1u << 10)) { o.tableBits = 10; o.skipLog = 4; o.maxLen = 4 << 10; }
+    else if (n > 32) { o.tableBits = 9; o.skipLog = 3; o.maxLen = 1 << 10; }
+    else return 0;
+    return encode_fast_asm(dst, src, (int)n, &o);
+}
+
 /* ---- L2: encode_l2.go:61-338 (long 17 bit hash7 / short 14 bit hash4) and
  *          encode_l2.go:343-596 (long 15 bit hash6 / short 12 bit hash4).
  * As for L1, one parameterised body: the 64K variant drops guards that cannot

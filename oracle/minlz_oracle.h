@@ -59,6 +59,11 @@ int mzo_emit_copy_lits3(uint8_t *dst, const uint8_t *lits, int nlits, int offset
 int64_t mzo_encode_block_l0(uint8_t *dst, const uint8_t *src, size_t n); /* LevelSuperFast, encode_l0.go */
 int64_t mzo_encode_block_l1(uint8_t *dst, const uint8_t *src, size_t n);
 int64_t mzo_encode_block_l2(uint8_t *dst, const uint8_t *src, size_t n);
+/* The same seam as built for amd64 (encode_amd64.go:37-189 -> the generated
+ * assembly of _generate/gen.go:257-1155), restated; byte-identical to the real
+ * assembly run through oracle/_ref (tests/test_ref_asm.py). */
+int64_t mzo_encode_block_l0_asm(uint8_t *dst, const uint8_t *src, size_t n);
+int64_t mzo_encode_block_l1_asm(uint8_t *dst, const uint8_t *src, size_t n);
 
 /* decode.go:178 minLZDecodeGo: dst_len must equal the decoded length, src is
  * the token stream without 0x00 + uvarint.  Returns 0 ok / 1 corrupt. */
