@@ -56,6 +56,26 @@ extern "C" {
 #define MZCU_BLOCK_OK 0
 #define MZCU_BLOCK_CORRUPT 1
 
+/* Encoder FLAVOUR.  The reference ships two implementations of its encode loops,
+ * selected at build time: the pure-Go functions (encode_l0/l1/l2.go; `-tags noasm`,
+ * purego, every platform without assembly -- asm_none.go:15) and the generated
+ * assembly (asm_amd64.s from _generate/gen.go; encode_amd64.go:15).  README.md:375:
+ * "Using assembly/non-assembly versions will often produce slightly different
+ * output".  Both are valid MinLZ; they differ in margins, bail-out tests, match
+ * extension at the block tail and per-size-class tables.  This library mirrors
+ * both, byte for byte:
+ *   MZCU_FLAVOR_GO     (default) == encodeBlockGo / encodeFastBlockGo / encodeBlockBetterGo
+ *   MZCU_FLAVOR_AMD64            == encodeBlockAsm* / encodeFastBlockAsm* (what `go build`
+ *                                   produces on amd64); LevelFastest and LevelSuperFast.
+ *                                   LevelBalanced has no amd64-flavour kernel yet: encode
+ *                                   calls at that level fail with MZCU_ERR_INVALID_LEVEL.
+ * The setting is process-wide, like the build tag it stands for.  Decoding is
+ * unaffected (decodeBlockAsm == minLZDecodeGo by the reference's own tests). */
+#define MZCU_FLAVOR_GO 0
+#define MZCU_FLAVOR_AMD64 1
+int mzcu_set_encoder_flavor(int flavor);
+int mzcu_get_encoder_flavor(void);
+
 int mzcu_abi_version(void);
 /* Thread-local message of the last failing call on this thread. */
 const char *mzcu_last_error(void);

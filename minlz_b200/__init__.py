@@ -28,6 +28,23 @@ LevelBalanced = 2
 _OK, _E_CORRUPT, _E_TOO_LARGE, _E_UNSUPPORTED, _E_LEVEL, _E_DST, _E_CUDA, _E_ARG = 0, -1, -2, -3, -4, -5, -6, -7
 
 
+# Encoder flavour (include/minlz_cuda.h): which of the reference's two builds the
+# encoder mirrors byte for byte -- the pure-Go functions (`noasm`) or the amd64 assembly.
+FlavorGo = 0
+FlavorAMD64 = 1
+
+
+def set_encoder_flavor(flavor):
+    """Process-wide, like the build tag it stands for (asm_none.go:15 / encode_amd64.go:15)."""
+    rc = _lib.load().mzcu_set_encoder_flavor(int(flavor))
+    if rc:
+        _raise(rc)
+
+
+def get_encoder_flavor():
+    return int(_lib.load().mzcu_get_encoder_flavor())
+
+
 class MinLZError(Exception):
     """Base of the errors mirrored from decode.go:29-40."""
 

@@ -8,6 +8,8 @@ SO_PATH = os.path.join(_HERE, "libminlz_cuda.so")
 # every symbol include/minlz_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
+    "mzcu_set_encoder_flavor": (C.c_int, [C.c_int]),
+    "mzcu_get_encoder_flavor": (C.c_int, []),
     "mzcu_abi_version": (C.c_int, []),
     "mzcu_last_error": (C.c_char_p, []),
     "mzcu_device_count": (C.c_int, []),

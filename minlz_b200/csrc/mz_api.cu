@@ -25,6 +25,9 @@
 
 namespace {
 
+// Encoder flavour (see minlz_cuda.h): process-wide, like the build tag it stands for.
+std::atomic<int> g_flavor{MZCU_FLAVOR_GO};
+
 thread_local char g_err[512] = "";
 thread_local float g_last_kernel_ms = 0.f;
 
@@ -190,17 +193,26 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
         TableWs ws;
         int rc = acquire_tables(st, (size_t)grid * mz::kEncL1Warps * mz::kEncL1WsBytesPerWarp, &ws);
         if (rc) return rc;
-        if (level == MZCU_LEVEL_FASTEST)
+        const bool amd64 = g_flavor.load(std::memory_order_relaxed) == MZCU_FLAVOR_AMD64;
+        if (level == MZCU_LEVEL_FASTEST && !amd64)
             mz::encode_l1_kernel<false><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(
                 nblk, src, sbeg, send, dst, dbeg, out_len, counter, static_cast<mz::Slot *>(ws.ptr), gate, slice);
-        else
+        else if (level == MZCU_LEVEL_FASTEST)
+            mz::encode_l1_asm_kernel<false><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(
+                nblk, src, sbeg, send, dst, dbeg, out_len, counter, static_cast<mz::Slot *>(ws.ptr), gate, slice);
+        else if (!amd64)
             mz::encode_l1_kernel<true><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(
+                nblk, src, sbeg, send, dst, dbeg, out_len, counter, static_cast<mz::Slot *>(ws.ptr), gate, slice);
+        else
+            mz::encode_l1_asm_kernel<true><<<grid, mz::kEncL1Warps * 32, 0, stream>>>(
                 nblk, src, sbeg, send, dst, dbeg, out_len, counter, static_cast<mz::Slot *>(ws.ptr), gate, slice);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaEventRecord(ws.done, stream);
         release_tables(st, ws);
         if (e != cudaSuccess) return fail(MZCU_ERR_CUDA, "encode_l1 launch: %s", cudaGetErrorString(e));
     } else if (level == MZCU_LEVEL_BALANCED) {
+        if (g_flavor.load(std::memory_order_relaxed) == MZCU_FLAVOR_AMD64)
+            return fail(MZCU_ERR_INVALID_LEVEL, "LevelBalanced has no amd64-flavour kernel yet (only MZCU_FLAVOR_GO)");
         if (gate) return fail(MZCU_ERR_INVALID_ARG, "encode_l2 has no arrival gate");
         int grid = (nblk + mz::kEncL2Warps - 1) / mz::kEncL2Warps;
         int resident = st.num_sms * st.enc_l2_ctas_per_sm;
@@ -775,6 +787,15 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
 extern "C" {
 
 int mzcu_abi_version(void) { return MZCU_ABI_VERSION; }
+
+int mzcu_set_encoder_flavor(int flavor) {
+    if (flavor != MZCU_FLAVOR_GO && flavor != MZCU_FLAVOR_AMD64)
+        return fail(MZCU_ERR_INVALID_ARG, "unknown encoder flavour %d", flavor);
+    g_flavor.store(flavor, std::memory_order_relaxed);
+    return MZCU_OK;
+}
+
+int mzcu_get_encoder_flavor(void) { return g_flavor.load(std::memory_order_relaxed); }
 const char *mzcu_last_error(void) { return g_err; }
 float mzcu_last_kernel_ms(void) { return g_last_kernel_ms; }
 

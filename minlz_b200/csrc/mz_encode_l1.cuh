@@ -80,6 +80,38 @@ __device__ __noinline__ int extend_forward8(const uint8_t *src, int s, int cand,
     }
 }
 
+// Asm flavour: matchLen (gen.go:3190-3288) -- the exact common prefix of src[s..] and
+// src[cand..], running to the END of the block (n), 8 bytes per lane per round.
+__device__ __noinline__ int extend_forward_exact(const uint8_t *src, int s, int cand, int n, int lane, const int *gate,
+                                                 int slice) {
+    int width = 4;
+    for (;;) {
+        if (s >= n) return n;
+        if (gate) gate_wait(gate, slice, min(s + 8 * width + 16, n));
+        const int pos = s + 8 * lane;
+        const bool act = lane < width;
+        const int valid = min(max(n - pos, 0), 8);  // bytes of this lane's word inside the block
+        uint64_t diff = 0;
+        if (act && valid == 8) {
+            diff = ldg_u64_unaligned(src + pos) ^ ldg_u64_unaligned(src + cand + 8 * lane);
+        } else if (act) {
+            for (int i = 0; i < valid; i++)
+                diff |= (uint64_t)(uint8_t)(src[pos + i] ^ src[cand + 8 * lane + i]) << (8 * i);
+            diff |= 1ull << (8 * valid);  // the byte at n never matches (valid < 8)
+        }
+        const unsigned stop = __ballot_sync(kFullMask, act && diff != 0);
+        if (stop == 0) {
+            s += 8 * width;
+            cand += 8 * width;
+            width = 32;
+            continue;
+        }
+        const int f = __ffs(stop) - 1;
+        const int add = __shfl_sync(kFullMask, (__ffsll((long long)diff) - 1) >> 3, f);
+        return s + 8 * f + add;
+    }
+}
+
 // Writes the low n bytes of tok at dst (n <= 8), one byte per lane.
 __device__ __forceinline__ void put_token(uint8_t *dst, uint64_t tok, int n, int lane) {
     if (lane < n) dst[lane] = (uint8_t)__byte_perm((uint32_t)tok, (uint32_t)(tok >> 32), lane);
@@ -90,10 +122,15 @@ __device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, int
 }
 
 // emitLiteral asm_none.go:84-122
-__device__ __forceinline__ int emit_literal(uint8_t *dst, const uint8_t *lit, int n, int lane) {
+// quirk: the 64 KiB Asm classes write runs of 286+ bytes with a 3-byte length (gen.go:2193-2200)
+__device__ __forceinline__ int emit_literal(uint8_t *dst, const uint8_t *lit, int n, int lane, bool quirk = false) {
     if (n == 0) return 0;
     int hn;
     uint64_t h = tok_literal_hdr((uint32_t)n, &hn);
+    if (quirk && hn == 3) {
+        hn = 4;
+        h = (h & ~0xffull) | (31u << 3 | kTagLiteral);
+    }
     put_token(dst, h, hn, lane);
     copy_bytes(dst + hn, lit, n, lane);
     return hn + n;
@@ -135,18 +172,100 @@ __device__ __forceinline__ int emit_copy_lits3(uint8_t *dst, const uint8_t *lits
     return n + nlits;
 }
 
-// LevelFastest: encode_l1.go:39-283 (large) and :285-524 (<= 64 KiB)
+// ---- walk parameters ----------------------------------------------------------
+// Two FLAVOURS of the same walk exist in the reference, chosen by build tags:
+//   Go    the pure-Go functions (`-tags noasm`, non-amd64/arm64 platforms):
+//         encode_l1.go / encode_l0.go, two size classes;
+//   Asm   what amd64 runs: the functions generated by _generate/gen.go:257-1155
+//         (asm_amd64.s encodeBlockAsm* / encodeFastBlockAsm*), seven size classes
+//         (gen.go:57-76, encode_amd64.go:37-189).  Same walk; it differs in the
+//         margins (sLimit = len-17, `>=` exits), the bail-out tests against dstLimit
+//         (gen.go:380-417), byte-exact match extension to the end of the block
+//         (matchLen, gen.go:632-654,859-887), the per-class table/skip/hash/step,
+//         a far-candidate clamp in the 8 MiB class (gen.go:466-490) and a
+//         3-byte literal length quirk in the 64 KiB class (gen.go:2193-2200).
+// The kernel body is written once over a parameter object: compile-time
+// constants for the hot classes, runtime fields for the small Asm classes.
+
+// LevelFastest, Go flavour: encode_l1.go:39-283 (large) and :285-524 (<= 64 KiB)
 template <bool kSmall>
 struct L1Params {
-    static constexpr int kTableBits = kSmall ? 13 : 15;
-    static constexpr int kSkipLog = kSmall ? 5 : 6;
-    static constexpr int kStep = 4;
-    static constexpr int kMaxFuseLits = kSmall ? kMaxCopy2Lits : kMaxCopy3Lits;
+    static constexpr bool kAsm = false;
     static constexpr int kMinMatch = 4;         // candidates are verified on 4 bytes
     static constexpr bool kBackExtend = true;   // :169-172
-    __device__ static __forceinline__ int dst_limit(int n) { return n - (n >> 5) - 6; }
-    __device__ static __forceinline__ uint32_t hash(uint64_t u) {
-        return kSmall ? hash5(u, kTableBits) : hash6(u, kTableBits);
+    __device__ __forceinline__ int table_bits() const { return kSmall ? 13 : 15; }
+    __device__ __forceinline__ int skip_log() const { return kSmall ? 5 : 6; }
+    __device__ __forceinline__ int step() const { return 4; }
+    __device__ __forceinline__ int max_fuse_lits() const { return kSmall ? kMaxCopy2Lits : kMaxCopy3Lits; }
+    __device__ __forceinline__ int s_limit(int n) const { return n - kInputMargin; }
+    __device__ __forceinline__ int dst_limit(int n) const { return n - (n >> 5) - 6; }
+    __device__ __forceinline__ int lit_overhead() const { return 0; }
+    __device__ __forceinline__ bool lit_quirk() const { return false; }
+    __device__ __forceinline__ uint32_t hash(uint64_t u) const { return kSmall ? hash5(u, 13) : hash6(u, 15); }
+};
+
+// LevelFastest, Asm flavour, blocks > 512 KiB (encodeBlockAsm2MB / encodeBlockAsm:
+// gen.go:58-59: 15 bits, skipLog 6, hash6, step 4) -- the benchmark's class.
+struct L1AsmBigParams {
+    static constexpr bool kAsm = true;
+    static constexpr int kMinMatch = 4;
+    static constexpr bool kBackExtend = true;
+    __device__ __forceinline__ int table_bits() const { return 15; }
+    __device__ __forceinline__ int skip_log() const { return 6; }
+    __device__ __forceinline__ int step() const { return 4; }
+    __device__ __forceinline__ int max_fuse_lits() const { return 3; }            // gen.go:907
+    __device__ __forceinline__ int s_limit(int n) const { return n - 17; }        // gen.go:369
+    __device__ __forceinline__ int dst_limit(int n) const { return n - 17 - (n >> 5); }  // gen.go:380-391
+    __device__ __forceinline__ int lit_overhead() const { return 4; }             // gen.go:1157-1169
+    __device__ __forceinline__ bool lit_quirk() const { return false; }
+    __device__ __forceinline__ uint32_t hash(uint64_t u) const { return hash6(u, 15); }
+};
+
+// Asm flavour, every other size class of gen.go:57-76 (runtime fields).
+// kMatch8 = the Fast (LevelSuperFast) options: 8-byte compares, hash8, no literal
+// fusing, no backward extension, dstLimit from len>>3 (gen.go:68).
+template <bool kMatch8>
+struct AsmClassParams {
+    static constexpr bool kAsm = true;
+    static constexpr int kMinMatch = kMatch8 ? 8 : 4;
+    static constexpr bool kBackExtend = !kMatch8;
+    int tb, sl, st, hb, ovh;
+    bool quirk;
+    __device__ __forceinline__ int table_bits() const { return tb; }
+    __device__ __forceinline__ int skip_log() const { return sl; }
+    __device__ __forceinline__ int step() const { return st; }
+    __device__ __forceinline__ int max_fuse_lits() const { return kMatch8 ? 0 : 3; }
+    __device__ __forceinline__ int s_limit(int n) const { return n - 17; }
+    __device__ __forceinline__ int dst_limit(int n) const { return n - 17 - (n >> (kMatch8 ? 3 : 5)); }
+    __device__ __forceinline__ int lit_overhead() const { return ovh; }
+    __device__ __forceinline__ bool lit_quirk() const { return quirk; }
+    __device__ __forceinline__ uint32_t hash(uint64_t u) const {
+        if (kMatch8) return hash8(u, tb);
+        return hb == 6 ? hash6(u, tb) : hb == 5 ? hash5(u, tb) : hash4(u, tb);
+    }
+    // encode_amd64.go:119-189 (encodeBlock) / :37-107 (encodeBlockFast) -> gen.go:57-76
+    __device__ static __forceinline__ AsmClassParams for_len(int n) {
+        AsmClassParams q;
+        q.st = kMatch8 ? 4 : 3;
+        q.hb = kMatch8 ? 8 : 6;
+        q.ovh = 4;
+        q.quirk = false;
+        if (n > (2 << 20)) {
+            q.tb = kMatch8 ? 14 : 15, q.sl = kMatch8 ? 5 : 6, q.st = 4;
+        } else if (n > (512 << 10)) {
+            q.tb = kMatch8 ? 13 : 15, q.sl = kMatch8 ? 5 : 6, q.st = 4;
+        } else if (n > (64 << 10)) {
+            q.tb = kMatch8 ? 13 : 14, q.sl = kMatch8 ? 5 : 6, q.st = 4;
+        } else if (n > (16 << 10)) {
+            q.tb = kMatch8 ? 12 : 13, q.sl = kMatch8 ? 4 : 5, q.quirk = true;   // maxLen == 64 KiB
+        } else if (n > (4 << 10)) {
+            q.tb = kMatch8 ? 11 : 12, q.sl = kMatch8 ? 4 : 5, q.hb = kMatch8 ? 8 : 5, q.ovh = 3;
+        } else if (n > (1 << 10)) {
+            q.tb = 10, q.sl = kMatch8 ? 4 : 5, q.hb = kMatch8 ? 8 : 4, q.ovh = 3;
+        } else {
+            q.tb = 9, q.sl = kMatch8 ? 3 : 4, q.hb = kMatch8 ? 8 : 4, q.ovh = 3;
+        }
+        return q;
     }
 };
 
@@ -154,14 +273,18 @@ struct L1Params {
 // with an 8-byte minimum match, hash8, no backward extension, extension from +8.
 template <bool kSmall>
 struct L0Params {
-    static constexpr int kTableBits = kSmall ? 12 : 13;
-    static constexpr int kSkipLog = kSmall ? 4 : 5;
-    static constexpr int kStep = kSmall ? 4 : 5;
-    static constexpr int kMaxFuseLits = kSmall ? kMaxCopy2Lits : kMaxCopy3Lits;
+    static constexpr bool kAsm = false;
     static constexpr int kMinMatch = 8;
     static constexpr bool kBackExtend = false;  // encode_l0.go:164 `for false && ...`
-    __device__ static __forceinline__ int dst_limit(int n) { return kSmall ? n - (n >> 4) - 32 : n - (n >> 3) - 6; }
-    __device__ static __forceinline__ uint32_t hash(uint64_t u) { return hash8(u, kTableBits); }
+    __device__ __forceinline__ int table_bits() const { return kSmall ? 12 : 13; }
+    __device__ __forceinline__ int skip_log() const { return kSmall ? 4 : 5; }
+    __device__ __forceinline__ int step() const { return kSmall ? 4 : 5; }
+    __device__ __forceinline__ int max_fuse_lits() const { return kSmall ? kMaxCopy2Lits : kMaxCopy3Lits; }
+    __device__ __forceinline__ int s_limit(int n) const { return n - kInputMargin; }
+    __device__ __forceinline__ int dst_limit(int n) const { return kSmall ? n - (n >> 4) - 32 : n - (n >> 3) - 6; }
+    __device__ __forceinline__ int lit_overhead() const { return 0; }
+    __device__ __forceinline__ bool lit_quirk() const { return false; }
+    __device__ __forceinline__ uint32_t hash(uint64_t u) const { return hash8(u, kSmall ? 12 : 13); }
 };
 
 // Backward extension, restating
@@ -298,6 +421,20 @@ __device__ __noinline__ uint32_t probe_forwarded(const uint32_t *ring_mem, int p
     return nzmask24(B + 1, A + 1) | bb << 24;
 }
 
+// Cold path of the Asm flavour's 8 MiB class: a far candidate is clamped to
+// s - 2162685 (gen.go:466-490) and matched THERE; the slot snapshot is of another
+// position, so compare straight from the source.  Same result layout as above.
+__device__ __noinline__ uint32_t probe_direct(const uint8_t *src, int n, int pos, int cand) {
+    uint32_t nz = 0;
+    for (int k = kSnapFwd - 1; k >= 0; k--) {
+        const uint8_t a = pos + k < n ? src[pos + k] : 0, b = cand + k < n ? src[cand + k] : 0;
+        nz = nz << 1 | (a != b);
+    }
+    uint32_t bb = 0;
+    while (bb < 4 && cand - 1 - (int)bb >= 0 && src[cand - 1 - bb] == src[pos - 1 - bb]) bb++;
+    return nz | bb << 24;
+}
+
 // Encodes one block with one warp.  Returns bytes written or 0.
 //
 // One iteration of the outer loop is one BATCH = one DRAM round trip: lane L
@@ -316,10 +453,13 @@ __device__ __noinline__ uint32_t probe_forwarded(const uint32_t *ring_mem, int p
 // are evaluated by the token writer with the same values of d, one batch late;
 // the result (0 = incompressible) is the same.
 template <class P>
-__device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Slot *table, uint32_t *ring_mem,
-                               const int lane, const int *gate, const int slice) {
-    const int sLimit = n - kInputMargin;
-    const int dstLimit = P::dst_limit(n);
+__device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, const int n, Slot *table,
+                               uint32_t *ring_mem, const int lane, const int *gate, const int slice) {
+    const int sLimit = prm.s_limit(n);
+    const int dstLimit = prm.dst_limit(n);
+    // Asm flavour, 8 MiB class: far candidates are clamped (search) / rejected one byte earlier (re-match)
+    constexpr int kClampDist = kMaxCopy3Offset - 2;  // gen.go:467-469: minPos = s - maxOffset + 2
+    const bool clamp_far = P::kAsm && n > (2 << 20);
     const int fill_limit = (n + 64 + kRingChunk - 1) & ~(kRingChunk - 1);
     constexpr uint32_t kMinMask = P::kMinMatch == 8 ? 0xffu : 0xfu;
 
@@ -332,7 +472,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         ring.fetch28(-4, w0);
         const uint4 ia = make_uint4(0, 0, w0[1], w0[2]);
         const uint4 ib = make_uint4(w0[3], w0[4], w0[5], w0[6]);
-        const int slots = 1 << P::kTableBits;
+        const int slots = 1 << prm.table_bits();
         for (int i = lane; i < slots; i += 32) slot_store(table + i, ia, ib);
         __syncwarp();
     }
@@ -358,21 +498,26 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         const int wbase = rematch ? s - 2 : s;
         // When the skip distance is long (incompressible data) only the first search
         // step can fall in the window: do not fetch slots nobody will consume.
-        const int K = (!rematch && ((s - nextEmit) >> P::kSkipLog) >= 24) ? 8 : 32;
+        const int K = (!rematch && ((s - nextEmit) >> prm.skip_log()) >= 24) ? 8 : 32;
         const int p = wbase + lane;
         const bool active = lane < K && !done;
         uint32_t W[7];  // src[p-4 .. p+24)
         uint32_t h = 0;
         uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
         uint32_t rep4 = 0;
+        uint64_t far8 = 0;  // src[p-kClampDist-2 .. +8): the three clamped candidates of this position
         const bool rep_lane = active && p >= repeat;
         if (!done) {
             ring.seek(wbase - 8);
             ring.ensure(min(wbase + 320, fill_limit), lane);
             ring.fetch28(p - 4, W);
-            h = P::hash((uint64_t)W[2] << 32 | W[1]);
+            h = prm.hash((uint64_t)W[2] << 32 | W[1]);
             if (active) slot_load(table + h, ea, eb);
             if (rep_lane) rep4 = ldg_u32_unaligned(src + p - repeat);
+            if (clamp_far && active && p >= kClampDist) {
+                const int lo = p - kClampDist - 2;
+                far8 = lo >= 0 ? ldg_u64_unaligned(src + lo) : ldg_u64_unaligned(src) << (8 * -lo);
+            }
         }
 
         // ---------------- the loads are in flight: write the queued tokens ----------------
@@ -384,16 +529,17 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             const int ne = emitted;
             emitted = end;
             const int length = end - base;
-            if (kind) {  // :94-145
-                if (d + (base - ne) > dstLimit) return 0;
-                d += emit_literal(dst + d, src + ne, base - ne, lane);
+            if (kind) {  // :94-145; Asm: gen.go:614-624 checkDst(litLen)
+                if (P::kAsm ? d + (base - ne) + prm.lit_overhead() >= dstLimit : d + (base - ne) > dstLimit) return 0;
+                d += emit_literal(dst + d, src + ne, base - ne, lane, prm.lit_quirk());
                 d += emit_repeat(dst + d, length, lane);
                 continue;
             }
+            if (P::kAsm && d >= dstLimit) return 0;  // gen.go:828 (and :1039 with the same d)
             if (ne != base) {  // :190-206
-                if (base - ne > P::kMaxFuseLits || rep < kMinCopy2Offset) {
-                    if (d + (end - ne) > dstLimit) return 0;
-                    d += emit_literal(dst + d, src + ne, base - ne, lane);
+                if (base - ne > prm.max_fuse_lits() || rep < kMinCopy2Offset) {
+                    if (P::kAsm ? d + (base - ne) + prm.lit_overhead() >= dstLimit : d + (end - ne) > dstLimit) return 0;
+                    d += emit_literal(dst + d, src + ne, base - ne, lane, prm.lit_quirk());
                     d += emit_copy(dst + d, rep, length, lane);
                 } else if (rep <= kMaxCopy2Offset) {
                     d += emit_copy_lits2(dst + d, src + ne, base - ne, rep, length, lane);
@@ -403,7 +549,8 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             } else {
                 d += emit_copy(dst + d, rep, length, lane);
             }
-            if (end < sLimit && d > dstLimit) return 0;  // :229, first thing the re-match loop does
+            // :229, first thing the re-match loop does; Asm: gen.go:955-975
+            if (end < sLimit && (P::kAsm ? d >= dstLimit : d > dstLimit)) return 0;
         }
         q_cnt = 0;
         if (done) break;
@@ -424,11 +571,31 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         const bool eqm = active && (nz & kMinMask) == 0;
         const int dist = p - cand;
         // search probe j of a step sees minSrcPos = t - maxCopy3Offset (:83): dist <= max + j
-        const unsigned E0 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset);
-        unsigned E1 = E0, E2 = E0;
-        if (n > kMaxCopy3Offset) {
-            E1 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset + 1);
-            E2 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset + 2);
+        unsigned E0, E1, E2, ER;  // hit of lane L as search probe 0 / 1 / 2 of a step, as re-match probe
+        if (clamp_far) {
+            // probe j sees minPos = t - kClampDist: a candidate at distance >= kClampDist + j is
+            // replaced by position p - j - kClampDist and its 4 / 8 bytes compared there (CMOV)
+            const uint64_t cur = (uint64_t)W[2] << 32 | W[1];
+            auto hitj = [&](int j) -> bool {
+                if (dist < kClampDist + j) return eqm;
+                const uint64_t cb = far8 >> (8 * (2 - j));
+                // the 8-byte compare of the Fast classes needs 2 more bytes than far8 holds for j = 0, 1
+                if (P::kMinMatch == 8)
+                    return active && ldg_u64_unaligned(src + p - j - kClampDist) == cur;
+                return active && (uint32_t)cb == (uint32_t)cur;
+            };
+            E0 = __ballot_sync(kFullMask, hitj(0));
+            E1 = __ballot_sync(kFullMask, hitj(1));
+            E2 = __ballot_sync(kFullMask, hitj(2));
+            ER = __ballot_sync(kFullMask, eqm && dist < kMaxCopy3Offset);  // gen.go:1007-1021: candidate > base - maxOffset
+        } else {
+            E0 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset);
+            E1 = E0, E2 = E0;
+            if (!P::kAsm && n > kMaxCopy3Offset) {
+                E1 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset + 1);
+                E2 = __ballot_sync(kFullMask, eqm && dist <= kMaxCopy3Offset + 2);
+            }
+            ER = E0;
         }
         const unsigned Brep = __ballot_sync(kFullMask, rep_lane && rep4 == W[1]);
 
@@ -454,6 +621,10 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
         // Go: s = base + min match, then 8-byte chunks while s <= n-8 (:181-188)
         auto match_end = [&](int base, int known, int f, int offset) -> int {
             int e = base + known;
+            if (P::kAsm) {  // matchLen to the end of the block (gen.go:859-887)
+                if (f == kSnapFwd && e < n) e = extend_forward_exact(src, e, e - offset, n, lane, gate, slice);
+                return min(e, n);
+            }
             if (f == kSnapFwd || e > n - 8) {
                 int q_stop = base + P::kMinMatch;
                 if (q_stop <= n - 8) q_stop += (((n - 8 - q_stop) >> 3) + 1) << 3;
@@ -479,7 +650,7 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                     if (L >= K) break;
                     int fcand = -1;
                     uint32_t fnz = 0;
-                    bool hit = (E0 >> L) & 1u;  // read before this step's inserts (:236-239)
+                    bool hit = (ER >> L) & 1u;  // read before this step's inserts (:236-239)
                     if ((dup >> L) & 1u) hit = probe_cold(L, ins, hit, &fcand, &fnz);
                     ins |= 5u << (L - 2);
                     if (!hit) {
@@ -514,8 +685,8 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             // ---- one search step at t (:70-160) ----
             const int t = s;
             const int L = t - wbase;
-            const int nextS = t + ((t - nextEmit) >> P::kSkipLog) + P::kStep;  // :79
-            if (nextS > sLimit) {
+            const int nextS = t + ((t - nextEmit) >> prm.skip_log()) + prm.step();  // :79
+            if (P::kAsm ? nextS >= sLimit : nextS > sLimit) {  // :80; Asm: gen.go:458-461 JAE
                 done = true;
                 break;
             }
@@ -531,8 +702,10 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
             if (rhit) {
                 ins |= 3u << L;
                 int base = t + 1;
-                base -= extend_backward(src, base - repeat, base, nextEmit, lane);
-                s = extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane, gate, slice);
+                // Go: both levels extend a repeat backwards; Asm: only with checkBack (gen.go:593)
+                if (!P::kAsm || P::kBackExtend) base -= extend_backward(src, base - repeat, base, nextEmit, lane);
+                s = P::kAsm ? extend_forward_exact(src, t + 5, t + 5 - repeat, n, lane, gate, slice)  // gen.go:632-660
+                            : extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane, gate, slice);
                 if (lane == q_cnt) {
                     q_base = base;
                     q_rep = repeat | 3 << 24;
@@ -592,6 +765,10 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
                 mcand = __shfl_sync(kFullMask, cand, mps - wbase);
                 mnz = __shfl_sync(kFullMask, nz, mps - wbase);
             }
+            if (clamp_far && fcand < 0 && mps - mcand >= kClampDist + (mps - t)) {  // matched at the clamped position
+                mcand = t - kClampDist;
+                mnz = probe_direct(src, n, mps, mcand);
+            }
             const int mbb = mnz >> 24;
             mnz &= 0xffffffu;
             const int f = mnz ? __ffs(mnz) - 1 : kSnapFwd;
@@ -626,9 +803,9 @@ __device__ int encode_l1_block(uint8_t *dst, const uint8_t *src, const int n, Sl
     }
 
     // emitRemainder (encode_l1.go:268-282)
-    if (nextEmit < n) {
-        if (d + n - nextEmit > dstLimit) return 0;
-        d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane);
+    if (nextEmit < n) {  // Asm: gen.go:1092-1119
+        if (P::kAsm ? d + (n - nextEmit) + prm.lit_overhead() >= dstLimit : d + n - nextEmit > dstLimit) return 0;
+        d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane, prm.lit_quirk());
     }
     return d;
 }
@@ -657,11 +834,47 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
         if (n64 >= kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {
             const int n = (int)n64;
             if (kSuperFast)
-                res = n <= 65536 ? encode_l1_block<L0Params<true>>(dp, sp, n, table, rings[warp], lane, gate, slice)
-                                 : encode_l1_block<L0Params<false>>(dp, sp, n, table, rings[warp], lane, gate, slice);
+                res = n <= 65536 ? encode_l1_block(L0Params<true>(), dp, sp, n, table, rings[warp], lane, gate, slice)
+                                 : encode_l1_block(L0Params<false>(), dp, sp, n, table, rings[warp], lane, gate, slice);
             else
-                res = n <= 65536 ? encode_l1_block<L1Params<true>>(dp, sp, n, table, rings[warp], lane, gate, slice)
-                                 : encode_l1_block<L1Params<false>>(dp, sp, n, table, rings[warp], lane, gate, slice);
+                res = n <= 65536 ? encode_l1_block(L1Params<true>(), dp, sp, n, table, rings[warp], lane, gate, slice)
+                                 : encode_l1_block(L1Params<false>(), dp, sp, n, table, rings[warp], lane, gate, slice);
+        }
+        if (lane == 0) out_len[blk] = (uint32_t)res;
+        __syncwarp();
+    }
+}
+
+// The same persistent kernel for the Asm flavour (MZCU_FLAVOR_AMD64): size-class
+// dispatch of encode_amd64.go:37-189.  A separate kernel so that the Go-flavour
+// kernel's register allocation and code size are untouched.
+template <bool kSuperFast>
+__global__ void __launch_bounds__(kEncL1Warps * 32, MZ_ENC_L1_MIN_CTAS)
+encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
+                     const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
+                     uint32_t *__restrict__ out_len, int *counter, Slot *tables, const int *gate, int slice) {
+    __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int gwarp = blockIdx.x * kEncL1Warps + warp;
+    Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
+    for (;;) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(counter, 1);
+        blk = __shfl_sync(kFullMask, blk, 0);
+        if (blk >= nblk) return;
+        const uint8_t *sp = src + sbeg[blk];
+        const int64_t n64 = (int64_t)(send[blk] - sbeg[blk]);
+        uint8_t *dp = dst + dbeg[blk];
+        int res = 0;
+        // encode_amd64.go:106,187: the smallest class needs len > 32 (Fast) / > 16
+        if (n64 > (kSuperFast ? 32 : kMinNonLiteralBlockSize) && n64 <= kMaxBlockSize) {
+            const int n = (int)n64;
+            if (!kSuperFast && n > (512 << 10))
+                res = encode_l1_block(L1AsmBigParams(), dp, sp, n, table, rings[warp], lane, gate, slice);
+            else
+                res = encode_l1_block(AsmClassParams<kSuperFast>::for_len(n), dp, sp, n, table, rings[warp], lane, gate,
+                                      slice);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
