@@ -186,6 +186,7 @@ def workload_config(args):
                         (args.blocks, args.block_size, args.kind,
                          {-1: "LevelSuperFast (encode_l0)", 1: "LevelFastest (encode_l1)", 2: "LevelBalanced (encode_l2)"}[args.level]),
             "blocks_per_gpu": args.blocks, "block_size": args.block_size, "level": args.level,
+            "encoder_flavor": getattr(args, "flavor", "amd64"),
             "cache": "inputs (%.1f GB per pass) larger than the 126 MB L2, no flush needed" %
                      (args.blocks * args.block_size / 1e9)}
 
@@ -201,12 +202,17 @@ def main():
     ap.add_argument("--kind", default="json")
     ap.add_argument("--level", type=int, default=1, choices=(-1, 1, 2),
                     help="1 = LevelFastest (headline), 2 = LevelBalanced, -1 = LevelSuperFast")
+    ap.add_argument("--flavor", default="auto", choices=("auto", "go", "amd64"),
+                    help="which reference build the encoder mirrors byte for byte: the amd64 assembly (what the "
+                         "reference arm runs on this box; default for levels -1/1) or the pure-Go functions")
     ap.add_argument("--cpu-blocks", type=int, default=1024, help="bounded sample for the CPU legs")
     ap.add_argument("--e2e-blocks", type=int, default=4096, help="blocks per e2e step (host buffers)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.flavor == "auto":
+        args.flavor = "go" if args.level == 2 else "amd64"
 
     if args.impl == "reference":
         run_reference(args)
@@ -230,6 +236,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     nblk, bs = args.blocks, args.block_size
+    mz.set_encoder_flavor(mz.FlavorAMD64 if args.flavor == "amd64" else mz.FlavorGo)
 
     # ---- synthetic input, resident in HBM; independent blocks shard by rank
     src = synth.make_blocks(args.kind, nblk, bs, device=dev, first=rank * nblk).reshape(-1)
@@ -279,6 +286,24 @@ def main():
     assert int((out_len <= 0).sum()) == 0, "encoder returned incompressible on compressible data"
     assert torch.equal(dec, src), "round trip mismatch"
     comp_bytes = int(coff[-1])
+    # encoder bytes against the checker (never timed here): the reference's real assembly when
+    # oracle/_ref is on the box and the flavour is amd64, else the oracle restatement of the flavour
+    parity = "round trip verified bit-exact before timing"
+    if rank == 0 and not args.no_cpu:
+        from oracle import binding as oracle_port
+        ref_engine, ref_kind, _ = cpu_engine()
+        picks = sorted({0, 1, nblk // 2, nblk - 1})
+        h_len = out_len.cpu().numpy()
+        for i in picks:
+            got = enc[i * cap:i * cap + int(h_len[i])].cpu().numpy().tobytes()
+            blk = src[i * bs:(i + 1) * bs].cpu().numpy()
+            if args.flavor == "amd64" and ref_kind == "reference":
+                want, who = ref_engine.encode_block(blk, args.level), "the reference's amd64 assembly (oracle/_ref)"
+            else:
+                want = oracle_port.encode_block(blk, args.level, flavor="asm" if args.flavor == "amd64" else "go")
+                who = "the oracle restatement of the %s flavour" % args.flavor
+            assert got == want, "encoder bytes differ from %s on block %d" % (who, i)
+        parity = "encoder bytes identical to %s on blocks %s; %s" % (who, picks, parity)
 
     if dist is not None:
         dist.barrier()
@@ -364,6 +389,8 @@ def main():
     dec_gbs = dec_bytes / (dec_ms / K * 1e-3) / 1e9
     dominant_is_enc = enc_ms >= dec_ms
     enc_kernel = {-1: "encode_l1_kernel<true> (L0 params)", 1: "encode_l1_kernel<false>", 2: "encode_l2_kernel"}[args.level]
+    if args.flavor == "amd64":
+        enc_kernel = enc_kernel.replace("encode_l1_kernel", "encode_l1_asm_kernel")
     enc_traffic = ncu_traffic("encode") if args.level == 1 else None  # the ncu capture is of the L1 headline
     roof = {"bound": "hbm", "kernel": enc_kernel if dominant_is_enc else "decode_pc_kernel",
             "achieved": round(enc_gbs if dominant_is_enc else dec_gbs, 3), "peak": peak, "unit": "GB/s",
@@ -401,7 +428,7 @@ def main():
         "roofline": roof, "roofline_decode": roof_dec, "roofline_encode": roof_enc,
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
         "gpu_launches": K * 4,  # per step: encode_l1, scan_lengths, pack_blocks, decode
-        "parity": "round trip verified bit-exact before timing",
+        "parity": parity,
     }
     print(json.dumps(line))
     if dist is not None:

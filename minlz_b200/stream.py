@@ -7,9 +7,11 @@ DecodeConcurrent/Reset and ReaderMaxBlockSize/ReaderIgnoreCRC/
 ReaderIgnoreStreamIdentifier) for the part of the stream format that carries
 block data: stream identifier, compressed chunks 0x02 (and 0x03 on read),
 uncompressed chunks 0x01, EOF 0x20, padding / skippable chunks on read
-(SPEC.md "STREAM FORMAT" sections 1-4.11).  Index, search tables, sidecars,
-padding on write and the Snappy/S2 fallback are out of scope (SURVEY 2, rows
-13-15, 23) and raise ErrUnsupported where a stream requires them.
+(SPEC.md "STREAM FORMAT" sections 1-4.11), and the seek index (SURVEY 8(f) N3:
+index.py; WriterAddIndex / WriterCreateIndex / CloseIndex on write, Skip /
+ReadSeeker.Seek / ReadAt on read -- reader.go:1034,1322-1489).  Search tables,
+sidecars, padding on write and the Snappy/S2 fallback are out of scope (SURVEY
+2, rows 13-15, 23) and raise ErrUnsupported where a stream requires them.
 
 Where the work happens: framing (a few header bytes per chunk) is host code as
 in the reference; the per-block work -- CRC-32C of the uncompressed block,
@@ -23,6 +25,7 @@ import io
 import numpy as np
 
 from . import _lib
+from .index import ErrUnexpectedEOF, Index
 from . import (ErrCorrupt, ErrInvalidLevel, ErrTooLarge, ErrUnsupported, LevelBalanced, LevelFastest, LevelSuperFast,
                LevelUncompressed, MinLZError, _raise)
 
@@ -115,6 +118,24 @@ def WriterConcurrency(n):
     return f
 
 
+def WriterAddIndex(b=True):
+    """writer.go:1194 WriterAddIndex: append the seek index to the end of the stream on Close."""
+    def f(w):
+        if b and not w.gen_index:
+            raise ValueError("WriterAddIndex: WriterCreateIndex has been called with false parameter")
+        w.append_index = b
+    return f
+
+
+def WriterCreateIndex(b=True):
+    """writer.go:1306 WriterCreateIndex: index generation can be disabled (network streams)."""
+    def f(w):
+        w.gen_index = b
+        if not b and w.append_index:
+            raise ValueError("WriterCreateIndex: Cannot disable when WriterAddIndex has been requested")
+    return f
+
+
 def WriterDevice(n):
     def f(w):
         w.device = n
@@ -129,6 +150,8 @@ class Writer:
         self.block_size = DEFAULT_BLOCK_SIZE
         self.concurrency = 0
         self.device = -1
+        self.gen_index = True       # writer.go:41
+        self.append_index = False
         for o in opts:
             o(self)
         if self.concurrency == 0:
@@ -142,6 +165,9 @@ class Writer:
         self.uncomp_written = 0
         self.written = 0
         self.closed = False
+        self.index = Index() if self.gen_index else None   # writer.go:191-202
+        if self.index is not None:
+            self.index.reset(self.block_size)
 
     # -- internals ---------------------------------------------------------
     def _out(self, b):
@@ -157,6 +183,8 @@ class Writer:
             return
         if not self.wrote_header:
             self.wrote_header = True
+            if self.index is not None:
+                self.index.add(self.written, 0)   # writer.go:241: the header item is indexed too -> entry (0, 0)
             self._out(make_header(self.block_size))
         bs = self.block_size
         per = self.concurrency * bs
@@ -183,6 +211,8 @@ class Writer:
             for i in range(nblk):
                 a, b = int(soff[i]), int(soff[i + 1])
                 c0, c1 = int(doff[i]), int(doff[i + 1])
+                if self.index is not None:   # writer.go:241,945: (stream offset of the chunk, uncompressed start)
+                    self.index.add(self.written + len(out), self.uncomp_written + a)
                 if c1 > c0:  # writer.go:680-696: compressed chunk = crc + uvarint(len) + tokens
                     lenhdr = _uvarint(b - a)
                     clen = 4 + len(lenhdr) + (c1 - c0)
@@ -240,13 +270,30 @@ class Writer:
             self.writer.flush()
 
     def Close(self):
-        """writer.go:1051-1074: flush, then the EOF chunk with the total uncompressed size."""
+        """writer.go:1033 Close: flush, EOF chunk, and the index when WriterAddIndex was given."""
+        self._close_index(self.append_index)
+
+    def CloseIndex(self):
+        """writer.go:1047 CloseIndex: Close and return the index (also appended with WriterAddIndex)."""
+        return self._close_index(True)
+
+    def _close_index(self, want):
+        """writer.go:1051-1127 closeIndex: flush, the EOF chunk with the total uncompressed size,
+        then the index chunk (returned; written only with WriterAddIndex)."""
         if self.closed:
-            return
+            return None
+        if want and self.index is None:
+            raise ValueError("index requested, but was asked to not generate one")
         self.Flush()
         body = _uvarint(self.uncomp_written)
         self._out(bytes([CHUNK_EOF, len(body), 0, 0]) + body)
+        index = None
+        if want:
+            index = self.index.appendTo(b"", self.uncomp_written, self.written)
+            if self.append_index:
+                self._out(index)
         self.closed = True
+        return index
 
     def Written(self):
         """writer.go:1041 Written: (uncompressed in, compressed out)."""
@@ -321,6 +368,8 @@ class Reader:
         self.read_header = self.ignore_stream_id
         self.max_block = self.max_block_org
         self.done = False
+        self.skip_left = 0   # Skip(): uncompressed bytes still to drop before delivering
+        self.index = None
 
     def _read_full(self, n, allow_eof):
         b = self.r.read(n) if n else b""
@@ -394,14 +443,21 @@ class Reader:
             if isinstance(res, Exception):
                 self.err = res
                 return
-            self.out += res
             self.block_start += len(res)
+            if self.skip_left:
+                drop = min(self.skip_left, len(res))
+                self.skip_left -= drop
+                res = res[drop:]
+            self.out += res
 
-    def _fill(self):
-        """Parses chunks until a batch is complete (or the stream ends), then decodes it."""
+    def _fill(self, budget=None):
+        """Parses chunks until a batch is complete (or the stream ends, or `budget`
+        uncompressed bytes are covered), then decodes it.  Blocks that a pending Skip
+        covers entirely are dropped without being decoded (reader.go:1107-1150)."""
         batch = []
+        covered = 0
         try:
-            while len(batch) < self.concurrency:
+            while len(batch) < self.concurrency and (budget is None or covered < budget or not batch):
                 hdr = self._read_full(4, not self.want_eof)
                 if hdr is None:
                     self.done = True
@@ -427,7 +483,12 @@ class Reader:
                     body = body[hl:]
                     if n == 0 or n < len(body):  # reader.go:327-333
                         raise ErrCorrupt()
+                    if not batch and self.skip_left >= n:
+                        self.skip_left -= n
+                        self.block_start += n
+                        continue
                     batch.append((ctype, crc, body, n))
+                    covered += n
                 elif ctype == CHUNK_UNCOMPRESSED:
                     if clen < 4:
                         raise ErrCorrupt()
@@ -435,7 +496,12 @@ class Reader:
                     if n > self.max_block:
                         raise ErrTooLarge()
                     buf = self._read_full(clen, False)
+                    if not batch and self.skip_left >= n:
+                        self.skip_left -= n
+                        self.block_start += n
+                        continue
                     batch.append((ctype, int.from_bytes(buf[:4], "little"), buf[4:], n))
+                    covered += n
                 elif ctype == CHUNK_LEGACY:
                     raise ErrUnsupported()  # Snappy/S2 fallback stays in host Go (reader.go:355-404)
                 elif ctype == CHUNK_EOF:
@@ -495,7 +561,7 @@ class Reader:
         A stream error is raised once the data decoded before it has been delivered
         (for n < 0 the partial data travels on the exception as `.partial`)."""
         while (n < 0 or len(self.out) < n) and self.err is None and not self.done:
-            self._fill()
+            self._fill(None if n < 0 else n - len(self.out))
         if n < 0:
             data = bytes(self.out)
             self.out = bytearray()
@@ -529,10 +595,132 @@ class Reader:
             if self.done:
                 return total
 
+    def Skip(self, n):
+        """reader.go:1034 Skip: drop the next n uncompressed bytes.  Blocks lying entirely
+        inside the skipped range are not decoded (and, as in the reference, not checked)."""
+        if n < 0:
+            raise ValueError("attempted negative skip")
+        if self.err is not None:
+            raise self.err
+        take = min(n, len(self.out))
+        del self.out[:take]
+        n -= take
+        if n == 0:
+            return
+        self.skip_left += n
+        while self.skip_left and self.err is None and not self.done:
+            self._fill(1)
+        if self.err is not None:
+            raise self.err
+        if self.skip_left:
+            self.skip_left = 0
+            self.err = ErrUnexpectedEOF()
+            raise self.err
+
+    def ReadSeeker(self, index=None):
+        """reader.go:1322 ReadSeeker: random access through a seek index -- the bytes given
+        here, else the index at the end of the (seekable) input."""
+        if index:
+            self.index = Index()
+            try:
+                self.index.Load(index)
+            except MinLZError as e:
+                raise ErrCantSeek("loading index returned: %s" % e)
+        if not (hasattr(self.r, "seek") and hasattr(self.r, "tell")):
+            raise ErrCantSeek("input stream isn't seekable")
+        if self.index is None:
+            pos = self.r.tell()
+            idx = Index()
+            try:
+                idx.LoadStream(self.r)
+            except ErrUnsupported:
+                raise ErrCantSeek("input stream does not contain an index")
+            except MinLZError as e:
+                raise ErrCantSeek("reading index returned: %s" % e)
+            finally:
+                self.r.seek(pos)
+            self.index = idx
+        return ReadSeeker(self)
+
     def DecodeConcurrent(self, w, concurrent=0):
         if concurrent > 0:
             self.concurrency = concurrent
         return self.WriteTo(w)
+
+
+class ErrCantSeek(MinLZError):
+    """reader.go ErrCantSeek{Reason}"""
+
+    def __init__(self, reason):
+        super().__init__("minlz: Can't seek because " + reason)
+
+
+class ReadSeeker:
+    """reader.go:1363-1491 ReadSeeker: Seek / ReadAt over an indexed stream.  A read after a seek
+    frames only the chunks that cover the requested range and decodes those blocks in one
+    batched GPU call (index -> pick blocks -> batch decode)."""
+
+    def __init__(self, reader):
+        self.Reader = reader
+        self.seek_src = reader.r
+
+    def Index(self):
+        return self.Reader.index
+
+    def Read(self, n=-1):
+        return self.Reader.Read(n)
+
+    read = Read
+
+    def _pos(self):
+        r = self.Reader
+        return r.block_start - len(r.out)
+
+    def Seek(self, offset, whence=io.SEEK_SET):
+        r = self.Reader
+        if r.err is not None:
+            raise r.err
+        if whence == io.SEEK_SET:
+            absolute = offset
+        elif whence == io.SEEK_CUR:
+            absolute = self._pos() + offset
+        elif whence == io.SEEK_END:
+            absolute = r.index.TotalUncompressed + offset
+        else:
+            raise ErrUnsupported()
+        if absolute < 0:
+            raise ValueError("seek before start of file")
+        # inside what is already decoded: no need to seek (reader.go:1417-1422)
+        lo = r.block_start - len(r.out)
+        if r.skip_left == 0 and lo <= absolute < r.block_start:
+            del r.out[:absolute - lo]
+            return absolute
+        c, u = r.index.Find(absolute)
+        self.seek_src.seek(c)
+        r.out = bytearray()
+        r.block_start = u
+        r.skip_left = 0
+        r.done = False
+        r.want_eof = False
+        # chunks are self-delimiting, so parsing may start at any indexed chunk; the stream
+        # identifier is only found (and then honoured) when the entry is offset 0
+        r.read_header = True
+        if absolute > u:
+            r.Skip(absolute - u)
+        return absolute
+
+    seek = Seek
+
+    def ReadAt(self, n, offset):
+        """reader.go:1469 ReadAt: n bytes at uncompressed offset; short only at the end of the stream."""
+        self.Seek(offset, io.SEEK_SET)
+        out = bytearray()
+        while len(out) < n:
+            b = self.Reader.Read(n - len(out))
+            if not b:
+                break
+            out += b
+        return bytes(out)
 
 
 def NewReader(r, *opts):
