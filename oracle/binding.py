@@ -34,7 +34,7 @@ def lib():
         L.mzo_max_encoded_len.restype = C.c_int64
         L.mzo_max_encoded_len.argtypes = [C.c_int64]
         for f in (L.mzo_encode_block_l0, L.mzo_encode_block_l1, L.mzo_encode_block_l2,
-                  L.mzo_encode_block_l0_asm, L.mzo_encode_block_l1_asm):
+                  L.mzo_encode_block_l0_asm, L.mzo_encode_block_l1_asm, L.mzo_encode_block_l2_asm):
             f.restype = C.c_int64
             f.argtypes = [u8p, u8p, C.c_size_t]
         L.mzo_decode_block.restype = C.c_int
@@ -87,7 +87,7 @@ def encode_block(src, level, flavor="go"):
     s = _in(src)
     dst = np.empty(s.size + 64, dtype=np.uint8)
     if flavor == "asm":
-        f = {-1: lib().mzo_encode_block_l0_asm, 1: lib().mzo_encode_block_l1_asm}[level]
+        f = {-1: lib().mzo_encode_block_l0_asm, 1: lib().mzo_encode_block_l1_asm, 2: lib().mzo_encode_block_l2_asm}[level]
     else:
         f = {-1: lib().mzo_encode_block_l0, 1: lib().mzo_encode_block_l1, 2: lib().mzo_encode_block_l2}[level]
     n = f(dst.ctypes.data, _ptr(s), s.size)

@@ -802,6 +802,185 @@ int64_t mzo_encode_block_l0_asm(uint8_t *dst, const uint8_t *src, size_t n) {
     return encode_fast_asm(dst, src, (int)n, &o);
 }
 
+/* ---- L2, AMD64-assembly flavour -------------------------------------------
+ * _generate/gen.go:1171-2038 genEncodeBetterBlockAsm(name, lTableBits, sTableBits,
+ * skipLog, lHashBytes, maxLen) with the per-class options of gen.go:78-88, selected
+ * by encode_amd64.go:201-271.  Differences from encodeBlockBetterGo: margins
+ * (sLimit = len-17 / len-8, `>=` exits), bail tests `dst + lits + overhead >=
+ * dstLimit` (gen.go:1490-1508,1716-1735), skip capped at maxSkip = 100 in the three
+ * large classes (gen.go:1327-1354), matchLen to the end of the block, the far
+ * 4-byte-match rejection at offset > 65599 (Go: > 65535) without an sLimit test
+ * (gen.go:1786-1801), candidates clamped (CMOV) in the 8 MiB class, the per-class
+ * tables and the 64 KiB literal quirk.  PINNED by tests/test_ref_asm.py against the
+ * real assembly. */
+typedef struct {
+    int lBits, sBits, skipLog, lHashBytes, maxLen, maxSkip, outMargin, inMargin;
+} better_opts;
+
+static int64_t encode_better_asm(uint8_t *dst, const uint8_t *src, int n, const better_opts *o) {
+    const int maxOffset = o->maxLen - 1;
+    const int clampFar = maxOffset > kMaxCopy3Offset;
+    const int litOverhead = o->maxLen < 30 ? 1 : o->maxLen < 256 ? 2 : o->maxLen < 65536 ? 3 : 4;
+    uint32_t *lTab = (uint32_t *)calloc(((size_t)1 << o->lBits) + ((size_t)1 << o->sBits), sizeof(uint32_t));
+    if (!lTab) return 0;
+    uint32_t *sTab = lTab + ((size_t)1 << o->lBits);
+    const int sLimit = n - o->inMargin;                                    /* gen.go:1272-1282 */
+    const int64_t dstLimit = (int64_t)(n - o->outMargin) - (n >> 5);       /* gen.go:1284-1297 */
+    int nextEmit = 0, s = 1, repeat = 1, nextS = 0;
+    int64_t d = 0;
+    int candidate, base, length, offset;
+    uint64_t cv;
+#define LH(v) hashNx((v), o->lBits, o->lHashBytes)
+#define SH(v) hashNx((v), o->sBits, 4)
+#define RET0() do { free(lTab); return 0; } while (0)
+#define CLAMP(c, minPos) do { if (clampFar && (c) <= (minPos)) (c) = (minPos); } while (0)
+
+search_loop:
+    {
+        uint32_t skip = (uint32_t)(s - nextEmit) >> o->skipLog;            /* gen.go:1324-1354 */
+        if (o->maxSkip == 0 || skip <= (uint32_t)(o->maxSkip - 1)) nextS = s + (int)skip + 1;
+        else nextS = s + o->maxSkip;
+        if ((uint32_t)nextS >= (uint32_t)sLimit) goto emit_remainder;
+        cv = ld64(src, s);
+        uint32_t hash0 = LH(cv), hash1 = SH(cv);
+        candidate = (int)lTab[hash0];
+        int candidateS = (int)sTab[hash1];
+        lTab[hash0] = (uint32_t)s;
+        sTab[hash1] = (uint32_t)s;
+        const int minPos = s - kMaxCopy3Offset + 2;                        /* gen.go:1396-1399 */
+        CLAMP(candidate, minPos);
+        const uint64_t longVal = ld64(src, candidate);
+        if (longVal == cv) goto candidate_match;                           /* gen.go:1425-1429 */
+        CLAMP(candidateS, minPos);
+        const uint64_t shortVal = ld64(src, candidateS);
+
+        if (((ld64(src, s - repeat) ^ cv) & (0xffffffffull << 8)) == 0) {  /* gen.go:1445-1459 */
+            base = s + 1;
+            for (int i = base - repeat; i != 0 && base > nextEmit && src[i - 1] == src[base - 1];) {
+                base--;
+                i--;
+            }
+            if (d + (base - nextEmit) + litOverhead >= dstLimit) RET0();   /* gen.go:1490-1508 */
+            if (nextEmit != base) {
+                d += emit_literal_asm(dst + d, src + nextEmit, (size_t)(base - nextEmit), o->maxLen);
+                nextEmit = base;
+            }
+            s += 5;
+            s += match_len_full(src, s, s - repeat, n - s);
+            d += mzo_emit_repeat(dst + d, s - base);
+            nextEmit = s;
+            if ((uint32_t)s >= (uint32_t)sLimit) goto emit_remainder;      /* gen.go:1576-1577 */
+            for (int64_t i0 = base + 1, i1 = s - 2; i0 < i1; i0 += 2, i1 -= 2) { /* gen.go:1587-1622 */
+                lTab[LH(ld64(src, i0))] = (uint32_t)i0;
+                sTab[SH(ld64(src, i0 + 1))] = (uint32_t)(i0 + 1);
+                lTab[LH(ld64(src, i1))] = (uint32_t)i1;
+                sTab[SH(ld64(src, i1 + 1))] = (uint32_t)(i1 + 1);
+            }
+            goto search_loop;
+        }
+        /* no_repeat_found, gen.go:1625-1690 */
+        if ((uint32_t)longVal == (uint32_t)cv) goto candidate_match;
+        if ((uint32_t)shortVal == (uint32_t)cv) {
+            /* short match at s: try a long candidate at s+1 */
+            cv >>= 8;
+            hash0 = LH(cv);
+            candidate = (int)lTab[hash0];
+            s++;
+            lTab[hash0] = (uint32_t)s;
+            CLAMP(candidate, minPos);
+            if (ld32(src, candidate) == (uint32_t)cv) goto candidate_match;
+            s--;
+            candidate = candidateS;
+            goto candidate_match;
+        }
+        s = nextS;
+        goto search_loop;
+    }
+
+candidate_match:
+    while (candidate != 0 && s > nextEmit && src[candidate - 1] == src[s - 1]) { /* gen.go:1696-1717 */
+        s--;
+        candidate--;
+    }
+    if (d + (s - nextEmit) + litOverhead >= dstLimit) RET0();              /* gen.go:1720-1737 */
+    base = s;
+    s += 4;
+    candidate += 4;
+    length = match_len_full(src, s, candidate, n - s);
+    offset = s - candidate;
+    if (maxOffset > kMaxCopy2Offset && length == 0 && offset > kMaxCopy2Offset && offset != repeat) {
+        s = nextS + 1;                                                     /* gen.go:1786-1801 */
+        goto search_loop;
+    }
+    repeat = offset;
+    {
+        const int litLen = base - nextEmit, ne = nextEmit;
+        s += length;
+        length += 4;
+        nextEmit = s;
+        if (litLen == 0) {
+            d += mzo_emit_copy(dst + d, offset, length);
+        } else if (offset < kMinCopy2Offset) {
+            d += emit_literal_asm(dst + d, src + ne, (size_t)litLen, o->maxLen);
+            d += mzo_emit_copy(dst + d, offset, length);
+        } else if (maxOffset > kMaxCopy2Offset && offset > kMaxCopy2Offset) { /* gen.go:1848-1866 */
+            if (litLen > 3) {
+                d += emit_literal_asm(dst + d, src + ne, (size_t)litLen, o->maxLen);
+                d += mzo_emit_copy(dst + d, offset, length);
+            } else {
+                d += mzo_emit_copy_lits3(dst + d, src + ne, litLen, offset, length);
+            }
+        } else if (litLen > 4) {
+            d += emit_literal_asm(dst + d, src + ne, (size_t)litLen, o->maxLen);
+            d += mzo_emit_copy(dst + d, offset, length);
+        } else {
+            d += mzo_emit_copy_lits2(dst + d, src + ne, litLen, offset, length); /* gen.go:1826-1846 */
+        }
+    }
+    if ((uint32_t)s >= (uint32_t)sLimit) goto emit_remainder;              /* gen.go:1899-1902 */
+    if (d >= dstLimit) RET0();                                             /* gen.go:1905-1918 */
+    {   /* index the match interior, gen.go:1921-1978 */
+        int64_t i0 = base + 1, i1 = s - 2;
+        lTab[LH(ld64(src, i0))] = (uint32_t)i0;
+        lTab[LH(ld64(src, i1))] = (uint32_t)i1;
+        sTab[SH(ld64(src, i0 + 1))] = (uint32_t)(i0 + 1);
+        sTab[SH(ld64(src, i1 + 1))] = (uint32_t)(i1 + 1);
+        int64_t i2 = (i0 + i1 + 1) >> 1;
+        i0 += 1;
+        i1 -= 1;
+        for (; i2 < i1; i0 += 2, i2 += 2) {
+            lTab[LH(ld64(src, i0))] = (uint32_t)i0;
+            lTab[LH(ld64(src, i2))] = (uint32_t)i2;
+        }
+    }
+    goto search_loop;
+
+emit_remainder:                                                            /* gen.go:1980-2017 */
+    free(lTab);
+    if (d + (n - nextEmit) + litOverhead >= dstLimit) return 0;
+    if (nextEmit != n) d += emit_literal_asm(dst + d, src + nextEmit, (size_t)(n - nextEmit), o->maxLen);
+    return d;
+#undef LH
+#undef SH
+#undef RET0
+#undef CLAMP
+}
+
+/* encode_amd64.go:201-271 encodeBlockBetter -> variants of gen.go:78-88 */
+int64_t mzo_encode_block_l2_asm(uint8_t *dst, const uint8_t *src, size_t n) {
+    if (n > MZO_MAX_BLOCK_SIZE) return 0;
+    better_opts o;
+    if (n > (2u << 20)) o = (better_opts){17, 14, 8, 7, 8 << 20, 100, 17, 17};
+    else if (n > (512u << 10)) o = (better_opts){17, 14, 7, 7, 2 << 20, 100, 17, 17};
+    else if (n > (64u << 10)) o = (better_opts){16, 13, 7, 7, 512 << 10, 100, 11, 8};
+    else if (n > (16u << 10)) o = (better_opts){15, 12, 6, 6, 64 << 10, 0, 11, 8};
+    else if (n > (4u << 10)) o = (better_opts){14, 11, 6, 6, 16 << 10, 0, 11, 8};
+    else if (n > (1u << 10)) o = (better_opts){12, 10, 5, 6, 4 << 10, 0, 11, 8};
+    else if (n > kMinNonLiteralBlockSize) o = (better_opts){11, 8, 4, 6, 1 << 10, 0, 11, 8};
+    else return 0;
+    return encode_better_asm(dst, src, (int)n, &o);
+}
+
 /* ---- L2: encode_l2.go:61-338 (long 17 bit hash7 / short 14 bit hash4) and
  *          encode_l2.go:343-596 (long 15 bit hash6 / short 12 bit hash4).
  * As for L1, one parameterised body: the 64K variant drops guards that cannot

@@ -64,6 +64,7 @@ int64_t mzo_encode_block_l2(uint8_t *dst, const uint8_t *src, size_t n);
  * assembly run through oracle/_ref (tests/test_ref_asm.py). */
 int64_t mzo_encode_block_l0_asm(uint8_t *dst, const uint8_t *src, size_t n);
 int64_t mzo_encode_block_l1_asm(uint8_t *dst, const uint8_t *src, size_t n);
+int64_t mzo_encode_block_l2_asm(uint8_t *dst, const uint8_t *src, size_t n);
 
 /* decode.go:178 minLZDecodeGo: dst_len must equal the decoded length, src is
  * the token stream without 0x00 + uvarint.  Returns 0 ok / 1 corrupt. */

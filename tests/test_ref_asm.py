@@ -8,9 +8,9 @@ What is pinned against real reference code, not against a restatement:
     (the reference's own TestCompareDecoders idea, decode_asm_test.go);
   * emitters and matchLen: == the assembly's emitLiteral/emitRepeat/emitCopy/
     emitCopyLits2/emitCopyLits3/matchLen on value grids;
-  * LevelFastest and LevelSuperFast encoders, amd64 flavour
-    (mzo_encode_block_l{1,0}_asm): BYTE-IDENTICAL to encodeBlockAsm* /
-    encodeFastBlockAsm* over every size class, corpus and bail-out case;
+  * all three encoders, amd64 flavour (mzo_encode_block_l{0,1,2}_asm):
+    BYTE-IDENTICAL to encodeFastBlockAsm* / encodeBlockAsm* / encodeBetterBlockAsm*
+    over every size class, corpus and bail-out case;
   * the Go-flavour encoders (the noasm build, what the default GPU mode mirrors):
     their streams decode to the input with the real decoder, and for blocks
     > 512 KiB the L1 Go flavour differs from the real assembly only in the tail
@@ -52,7 +52,7 @@ def _split_block(blob):
 
 
 def _same_encoders(oracle, data, tag):
-    for level in (-1, 1):
+    for level in (-1, 1, 2):
         want = refasm.encode_block(data, level)
         got = oracle.encode_block(data, level, flavor="asm")
         assert got == want, "level %d %s: restated %d B vs assembly %d B" % (level, tag, len(got), len(want))
@@ -210,7 +210,7 @@ def test_encoders_identical_bailouts(oracle):
     puts the output next to dstLimit, so every bail test (gen.go:395-417) fires somewhere;
     plus literal runs of 286+ bytes in the 16K-64K class (the 3-byte-length quirk)."""
     rng = np.random.default_rng(11)
-    hits = [0, 0, 0]
+    hits = [0, 0, 0, 0]   # [cases, level 1, level 2, level -1]
     for n in (600, 3000, 12000, 50000, 200000, 600000, 1 << 20):
         for dens in (0.0, 0.05, 0.08, 0.1, 0.12, 0.15, 0.2, 0.3, 0.4, 0.5, 0.6, 0.8):
             d = rng.integers(0, 256, n, dtype=np.uint8)
@@ -219,14 +219,14 @@ def test_encoders_identical_bailouts(oracle):
                 q = int(rng.integers(0, p - 48))
                 d[p:p + 48] = d[q:q + 48]
             _same_encoders(oracle, d, ("bail", n, dens))
-            for level in (-1, 1):
+            for level in (-1, 1, 2):
                 hits[level] += refasm.encode_block(d, level) == b""
             hits[0] += 1
-    assert 5 < hits[1] < hits[0] - 5 and 5 < hits[-1] < hits[0] - 5, hits
+    assert all(5 < hits[lv] < hits[0] - 5 for lv in (-1, 1, 2)), hits
 
 
 def test_l2_assembly_round_trips(oracle):
-    # LevelBalanced assembly: no restated amd64 flavour yet; its streams must decode with both decoders
+    # LevelBalanced assembly streams decode with both decoders
     for kind, n in (("json", 1 << 20), ("text", 300000), ("binary", 40000), ("log", 3 << 20)):
         blk = synth.make_blocks(kind, 1, n).numpy()[0]
         enc = refasm.encode_block(blk, 2)
