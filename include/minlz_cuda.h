@@ -65,10 +65,8 @@ extern "C" {
  * extension at the block tail and per-size-class tables.  This library mirrors
  * both, byte for byte:
  *   MZCU_FLAVOR_GO     (default) == encodeBlockGo / encodeFastBlockGo / encodeBlockBetterGo
- *   MZCU_FLAVOR_AMD64            == encodeBlockAsm* / encodeFastBlockAsm* (what `go build`
- *                                   produces on amd64); LevelFastest and LevelSuperFast.
- *                                   LevelBalanced has no amd64-flavour kernel yet: encode
- *                                   calls at that level fail with MZCU_ERR_INVALID_LEVEL.
+ *   MZCU_FLAVOR_AMD64            == encodeFastBlockAsm* / encodeBlockAsm* / encodeBetterBlockAsm*
+ *                                   (what `go build` produces on amd64), every size class.
  * The setting is process-wide, like the build tag it stands for.  Decoding is
  * unaffected (decodeBlockAsm == minLZDecodeGo by the reference's own tests). */
 #define MZCU_FLAVOR_GO 0

@@ -211,8 +211,6 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
         release_tables(st, ws);
         if (e != cudaSuccess) return fail(MZCU_ERR_CUDA, "encode_l1 launch: %s", cudaGetErrorString(e));
     } else if (level == MZCU_LEVEL_BALANCED) {
-        if (g_flavor.load(std::memory_order_relaxed) == MZCU_FLAVOR_AMD64)
-            return fail(MZCU_ERR_INVALID_LEVEL, "LevelBalanced has no amd64-flavour kernel yet (only MZCU_FLAVOR_GO)");
         if (gate) return fail(MZCU_ERR_INVALID_ARG, "encode_l2 has no arrival gate");
         int grid = (nblk + mz::kEncL2Warps - 1) / mz::kEncL2Warps;
         int resident = st.num_sms * st.enc_l2_ctas_per_sm;
@@ -220,8 +218,12 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
         TableWs ws;
         int rc = acquire_tables(st, (size_t)grid * mz::kEncL2Warps * mz::kEncL2WsBytesPerWarp, &ws);
         if (rc) return rc;
-        mz::encode_l2_kernel<<<grid, mz::kEncL2Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len, counter,
-                                                                       static_cast<uint32_t *>(ws.ptr));
+        if (g_flavor.load(std::memory_order_relaxed) == MZCU_FLAVOR_AMD64)
+            mz::encode_l2_asm_kernel<<<grid, mz::kEncL2Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len,
+                                                                               counter, static_cast<uint32_t *>(ws.ptr));
+        else
+            mz::encode_l2_kernel<<<grid, mz::kEncL2Warps * 32, 0, stream>>>(nblk, src, sbeg, send, dst, dbeg, out_len, counter,
+                                                                           static_cast<uint32_t *>(ws.ptr));
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaEventRecord(ws.done, stream);
         release_tables(st, ws);

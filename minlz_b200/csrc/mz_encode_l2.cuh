@@ -258,6 +258,234 @@ emit_remainder:  // :329-337
     return d;
 }
 
+// ---- Asm flavour (MZCU_FLAVOR_AMD64) -----------------------------------------
+// What amd64 runs for LevelBalanced: the functions generated by
+// _generate/gen.go:1171-2038 genEncodeBetterBlockAsm, seven size classes
+// (gen.go:78-88, encode_amd64.go:201-271).  Same walk as encodeBlockBetterGo; it
+// differs in the margins (sLimit = len-17 or len-8, `>=` exits), the bail-out tests
+// `d + lits + overhead >= dstLimit` (gen.go:1490-1508,1720-1737,1905-1918,1984-2003),
+// the skip cap of 100 in the three large classes (gen.go:1327-1354), the far
+// 4-byte-match rejection at offset > 65599 with no sLimit test (gen.go:1786-1801),
+// candidates clamped to s-2162685 in the 8 MiB class (gen.go:1396-1419), per-class
+// tables / hashes and the 64 KiB literal quirk (gen.go:2193-2200).
+struct BetterAsmClass {
+    int lBits, sBits, skipLog, lHashBytes, maxSkip, outMargin, inMargin, ovh;
+    bool quirk, far3, clamp;
+    __device__ __forceinline__ uint32_t hashL(uint64_t u) const { return lHashBytes == 7 ? hash7(u, lBits) : hash6(u, lBits); }
+    __device__ __forceinline__ uint32_t hashS(uint64_t u) const { return hash4(u, sBits); }
+    __device__ static __forceinline__ BetterAsmClass for_len(int n) {
+        BetterAsmClass q;
+        q.lHashBytes = 7, q.maxSkip = 100, q.outMargin = 17, q.inMargin = 17, q.ovh = 4;
+        q.quirk = false, q.far3 = true, q.clamp = false;
+        if (n > (2 << 20)) {
+            q.lBits = 17, q.sBits = 14, q.skipLog = 8, q.clamp = true;
+        } else if (n > (512 << 10)) {
+            q.lBits = 17, q.sBits = 14, q.skipLog = 7;
+        } else {
+            q.outMargin = 11, q.inMargin = 8;
+            if (n > (64 << 10)) {
+                q.lBits = 16, q.sBits = 13, q.skipLog = 7;
+            } else {
+                q.maxSkip = 0, q.lHashBytes = 6, q.far3 = false;
+                if (n > (16 << 10)) q.lBits = 15, q.sBits = 12, q.skipLog = 6, q.quirk = true;
+                else if (n > (4 << 10)) q.lBits = 14, q.sBits = 11, q.skipLog = 6, q.ovh = 3;
+                else if (n > (1 << 10)) q.lBits = 12, q.sBits = 10, q.skipLog = 5, q.ovh = 3;
+                else q.lBits = 11, q.sBits = 8, q.skipLog = 4, q.ovh = 3;
+            }
+        }
+        return q;
+    }
+};
+
+__device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const uint8_t *src, const int n,
+                                   uint32_t *lTable, uint32_t *sTable, const int lane) {
+    const int sLimit = n - P.inMargin;                    // gen.go:1272-1282
+    const int dstLimit = n - P.outMargin - (n >> 5);      // gen.go:1284-1297
+    int nextEmit = 0;
+    int s = 1;
+    int repeat = 1;
+    int d = 0;
+
+    for (;;) {
+        // ---- search_loop (gen.go:1307-1690) ----
+        const uint32_t skip = (uint32_t)(s - nextEmit) >> P.skipLog;
+        const int nextS = (P.maxSkip == 0 || skip <= (uint32_t)(P.maxSkip - 1)) ? s + (int)skip + 1 : s + P.maxSkip;
+        if (nextS >= sLimit) break;
+        const uint64_t cv = ldg_u64_unaligned(src + s);
+        const int minPos = s - kMaxCopy3Offset + 2;
+        // lane 0: long(cv)  lane 1: short(cv)  lane 2: repeat  lane 3: long(cv>>8) (used only behind a short hit)
+        uint32_t h = 0;
+        int c = 0;
+        if (lane == 0) h = P.hashL(cv);
+        if (lane == 1) h = P.hashS(cv);
+        if (lane == 3) h = P.hashL(cv >> 8);
+        const uint32_t hL = __shfl_sync(kFullMask, h, 0);
+        if (lane == 0 || lane == 3) c = (int)lTable[h];
+        if (lane == 1) c = (int)sTable[h];
+        if (lane == 3 && h == hL) c = s;  // lTab[hash0] = s is stored before the s+1 probe reads
+        __syncwarp();
+        if (lane == 0) lTable[h] = (uint32_t)s;
+        if (lane == 1) sTable[h] = (uint32_t)s;
+        if (P.clamp && c <= minPos) c = minPos;  // CMOVLLE: compared (and matched) at the clamped position
+        uint64_t v = 0;
+        if (lane < 2) v = ldg_u64_unaligned(src + c);
+        if (lane == 2) v = ldg_u64_unaligned(src + s - repeat);
+        if (lane == 3) v = ldg_u32_unaligned(src + c);
+        bool f8 = false, f4 = false;
+        if (lane == 0) {
+            f8 = cv == v;
+            f4 = (uint32_t)cv == (uint32_t)v;
+        } else if (lane == 1) {
+            f4 = (uint32_t)cv == (uint32_t)v;
+        } else if (lane == 2) {
+            f4 = ((cv ^ v) & (0xffffffffull << 8)) == 0;
+        } else if (lane == 3) {
+            f4 = (uint32_t)(cv >> 8) == (uint32_t)v;
+        }
+        const unsigned m8 = __ballot_sync(kFullMask, f8);
+        const unsigned m4 = __ballot_sync(kFullMask, f4);
+
+        int candidate;
+        if (m8 & 1u) {
+            candidate = __shfl_sync(kFullMask, c, 0);
+        } else if (m4 & 4u) {  // repeat at s+1 (gen.go:1445-1622)
+            int base = s + 1;
+            base -= extend_backward(src, base - repeat, base, nextEmit, lane);
+            if (d + (base - nextEmit) + P.ovh >= dstLimit) return 0;
+            d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane, P.quirk);
+            s = extend_to_end(src, n, s + 5, s + 5 - repeat, lane);
+            d += emit_repeat(dst + d, s - base, lane);
+            nextEmit = s;
+            if (s >= sLimit) break;
+            for (int i0 = base + 1, i1 = s - 2; i0 < i1; i0 += 2, i1 -= 2) {
+                const uint64_t a0 = ldg_u64_unaligned(src + i0), a1 = ldg_u64_unaligned(src + i0 + 1);
+                const uint64_t b0 = ldg_u64_unaligned(src + i1), b1 = ldg_u64_unaligned(src + i1 + 1);
+                if (lane == 0) {
+                    lTable[P.hashL(a0)] = (uint32_t)i0;
+                    sTable[P.hashS(a1)] = (uint32_t)(i0 + 1);
+                    lTable[P.hashL(b0)] = (uint32_t)i1;
+                    sTable[P.hashS(b1)] = (uint32_t)(i1 + 1);
+                }
+            }
+            __syncwarp();
+            continue;
+        } else if (m4 & 1u) {
+            candidate = __shfl_sync(kFullMask, c, 0);
+        } else if (m4 & 2u) {  // short match: try the long table at s+1 (gen.go:1665-1687)
+            if (lane == 3) lTable[h] = (uint32_t)(s + 1);
+            __syncwarp();
+            if (m4 & 8u) {
+                candidate = __shfl_sync(kFullMask, c, 3);
+                s++;
+            } else {
+                candidate = __shfl_sync(kFullMask, c, 1);
+            }
+        } else {
+            s = nextS;
+            continue;
+        }
+
+        // ---- candidate_match (gen.go:1692-1918) ----
+        {
+            const int back = extend_backward(src, candidate, s, nextEmit, lane);
+            candidate -= back;
+            s -= back;
+        }
+        if (d + (s - nextEmit) + P.ovh >= dstLimit) return 0;
+        const int base = s;
+        const int offset = base - candidate;
+        s = extend_to_end(src, n, s + 4, candidate + 4, lane);
+        if (P.far3 && s - base == 4 && offset > kMaxCopy2Offset && offset != repeat) {  // gen.go:1786-1801
+            s = nextS + 1;
+            continue;
+        }
+        repeat = offset;
+        {
+            const int nlits = base - nextEmit, length = s - base;
+            if (nlits == 0) {
+                d += emit_copy(dst + d, offset, length, lane);
+            } else if (offset < kMinCopy2Offset) {
+                d += emit_literal(dst + d, src + nextEmit, nlits, lane, P.quirk);
+                d += emit_copy(dst + d, offset, length, lane);
+            } else if (P.far3 && offset > kMaxCopy2Offset) {
+                if (nlits > 3) {
+                    d += emit_literal(dst + d, src + nextEmit, nlits, lane, P.quirk);
+                    d += emit_copy(dst + d, offset, length, lane);
+                } else {
+                    d += emit_copy_lits3(dst + d, src + nextEmit, nlits, offset, length, lane);
+                }
+            } else if (nlits > 4) {
+                d += emit_literal(dst + d, src + nextEmit, nlits, lane, P.quirk);
+                d += emit_copy(dst + d, offset, length, lane);
+            } else {
+                d += emit_copy_lits2(dst + d, src + nextEmit, nlits, offset, length, lane);
+            }
+        }
+        nextEmit = s;
+        if (s >= sLimit) break;
+        if (d >= dstLimit) return 0;
+        {   // index the match interior (gen.go:1921-1978); one lane keeps "later write wins"
+            int i0 = base + 1, i1 = s - 2;
+            const uint64_t a0 = ldg_u64_unaligned(src + i0), a1 = ldg_u64_unaligned(src + i0 + 1);
+            const uint64_t b0 = ldg_u64_unaligned(src + i1), b1 = ldg_u64_unaligned(src + i1 + 1);
+            if (lane == 0) {
+                lTable[P.hashL(a0)] = (uint32_t)i0;
+                lTable[P.hashL(b0)] = (uint32_t)i1;
+                sTable[P.hashS(a1)] = (uint32_t)(i0 + 1);
+                sTable[P.hashS(b1)] = (uint32_t)(i1 + 1);
+            }
+            int i2 = (i0 + i1 + 1) >> 1;
+            i0 += 1;
+            i1 -= 1;
+            for (; i2 < i1; i0 += 2, i2 += 2) {
+                const uint64_t a = ldg_u64_unaligned(src + i0), b = ldg_u64_unaligned(src + i2);
+                if (lane == 0) {
+                    lTable[P.hashL(a)] = (uint32_t)i0;
+                    lTable[P.hashL(b)] = (uint32_t)i2;
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // emit_remainder (gen.go:1980-2017): the bail test runs even when nothing is left
+    if (d + (n - nextEmit) + P.ovh >= dstLimit) return 0;
+    d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane, P.quirk);
+    return d;
+}
+
+__global__ void __launch_bounds__(kEncL2Warps * 32)
+encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
+                     const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
+                     uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
+    const int lane = lane_id();
+    const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
+    uint32_t *lTable = tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4);
+    uint32_t *sTable = lTable + (1 << 17);
+    for (;;) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(counter, 1);
+        blk = __shfl_sync(kFullMask, blk, 0);
+        if (blk >= nblk) return;
+        const uint8_t *sp = src + sbeg[blk];
+        const int64_t n64 = (int64_t)(send[blk] - sbeg[blk]);
+        uint8_t *dp = dst + dbeg[blk];
+        int res = 0;
+        if (n64 > kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {  // encode_amd64.go:260
+            const int n = (int)n64;
+            const BetterAsmClass cls = BetterAsmClass::for_len(n);
+            uint4 *t4 = reinterpret_cast<uint4 *>(lTable);
+            for (int i = lane; i < (1 << cls.lBits) / 4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+            uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
+            for (int i = lane; i < (1 << cls.sBits) / 4; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            res = encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, lane);
+        }
+        if (lane == 0) out_len[blk] = (uint32_t)res;
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(kEncL2Warps * 32)
 encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,

@@ -1,9 +1,9 @@
 """GPU parity of the amd64 FLAVOUR (MZCU_FLAVOR_AMD64): the CUDA encoders must be
 byte-identical to what the reference produces on amd64 -- its generated assembly
-(asm_amd64.s encodeBlockAsm* / encodeFastBlockAsm*).
+(asm_amd64.s encodeFastBlockAsm* / encodeBlockAsm* / encodeBetterBlockAsm*).
 
 Two checkers, both test infrastructure:
-  * the oracle's restated amd64 flavour (mzo_encode_block_l{1,0}_asm), which
+  * the oracle's restated amd64 flavour (mzo_encode_block_l{0,1,2}_asm), which
     tests/test_ref_asm.py pins byte-for-byte to the real assembly;
   * the real assembly itself through oracle/_ref/libminlz_ref.so whenever that
     library travelled to this box (built in the dev container from
@@ -45,7 +45,7 @@ def _cat(blobs):
     return flat, off
 
 
-def _check(oracle, items, levels=(-1, 1)):
+def _check(oracle, items, levels=(-1, 1, 2)):
     """items: [(tag, bytes-like)].  GPU amd64 flavour == restated flavour == real assembly."""
     raws = [bytes(d) for _, d in items]
     src, soff = _cat(raws)
@@ -115,7 +115,7 @@ def test_flavour_bailouts(oracle):
                 d[p:p + 48] = d[q:q + 48]
             items.append((("bail", n, dens), d.tobytes()))
     _check(oracle, items)
-    for level in (-1, 1):
+    for level in (-1, 1, 2):
         zero = sum(1 for _, d in items if not oracle.encode_block(d, level, flavor="asm"))
         assert 5 < zero < len(items) - 5, (level, zero)
 
@@ -133,10 +133,29 @@ def test_flavour_block_api_and_decode(oracle):
         assert mz.Decode(None, enc) == data
 
 
-def test_flavour_balanced_is_refused():
-    data = synth.make_blocks("json", 1, 1 << 16).numpy()[0].tobytes()
-    with pytest.raises(mz.ErrInvalidLevel):
-        mz.Encode(None, data, mz.LevelBalanced)
+def test_flavour_stream_writer_default_level(oracle):
+    """The Writer at its default level (LevelBalanced, writer.go:40) under the amd64 flavour: every
+    compressed chunk carries the assembly's tokens; the stream reads back."""
+    import io
+    from minlz_b200 import stream as mzs
+    data = synth.make_blocks("log", 1, 3 << 20).numpy()[0].tobytes() + b"tail"
+    bs = 256 << 10
+    buf = io.BytesIO()
+    w = mzs.NewWriter(buf, mzs.WriterBlockSize(bs))
+    w.EncodeBuffer(data)
+    w.Close()
+    blob = buf.getvalue()
+    pos, k = 10, 0
+    while blob[pos] == 0x02:
+        clen = int.from_bytes(blob[pos + 1:pos + 4], "little")
+        body = blob[pos + 8:pos + 4 + clen]
+        blk = data[k * bs:(k + 1) * bs]
+        tok = oracle.encode_block(blk, 2, flavor="asm")
+        assert body.endswith(tok) and len(body) - len(tok) <= 4, k
+        pos += 4 + clen
+        k += 1
+    assert k == 12 and blob[pos] == 0x01          # the 4-byte tail block is stored (len < 17)
+    assert mzs.NewReader(io.BytesIO(blob)).Read() == data
 
 
 def test_flavour_full_size_batch(oracle):

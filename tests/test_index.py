@@ -189,7 +189,9 @@ def test_seeking_with_appended_index():
     assert w.Written() == (len(data), len(blob))
     assert mzs.NewReader(io.BytesIO(blob)).Read() == data           # the index chunk is skippable
     rs = mzs.NewReader(io.BytesIO(blob)).ReadSeeker()
-    assert rs.Index().TotalUncompressed == len(data) and rs.Index().TotalCompressed == len(blob)
+    # writer.go:1084-1088: the compressed total is taken before the index chunk is appended
+    idx_len = int.from_bytes(blob[-10:-6], "little")
+    assert rs.Index().TotalUncompressed == len(data) and rs.Index().TotalCompressed == len(blob) - idx_len
     rng = np.random.default_rng(3)
     offs = [0, 1, (64 << 10) - 1, 64 << 10, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, len(data) - 1, len(data)]
     offs += [int(x) for x in rng.integers(0, len(data), 12)]
@@ -231,8 +233,12 @@ def test_index_stream_equals_writer_index():
     a.Load(own)
     b.Load(made)
     assert (a.TotalUncompressed, a.TotalCompressed) == (b.TotalUncompressed, b.TotalCompressed) == (len(data), len(blob))
-    # the writer's first entry is the stream header (0, 0); IndexStream's the first data chunk (10, 0)
-    assert a.Offsets[0] == (0, 0) and b.Offsets[0] == (10, 0) and a.Offsets[1:] == b.Offsets[1:]
+    # the writer's first entry is the stream header (0, 0) and it spaces entries >= 1 MiB apart
+    # (index.go:59-61); IndexStream starts at the first data chunk (10, 0) and spaces them by the
+    # first block's size (index.go:492-495).  Same chunk boundaries either way.
+    assert a.Offsets[0] == (0, 0) and b.Offsets[0] == (10, 0)
+    assert set(a.Offsets[1:]) <= set(b.Offsets) and len(a.Offsets) == 4 and len(b.Offsets) == 64
+    assert [u for _, u in b.Offsets] == [k << 16 for k in range(64)]
     rs = mzs.NewReader(io.BytesIO(blob)).ReadSeeker(made)
     for off in (0, 70000, (3 << 20) - 5, (3 << 20) + 12345, len(data) - 3):
         assert rs.ReadAt(4096, off) == data[off:off + 4096]
