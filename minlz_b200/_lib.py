@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libminlz_cuda.so")
+# MINLZ_CUDA_SO: an experiment / profiling build of the same library (build.build_variant)
+SO_PATH = os.environ.get("MINLZ_CUDA_SO") or os.path.join(_HERE, "libminlz_cuda.so")
 
 # every symbol include/minlz_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p

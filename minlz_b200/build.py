@@ -35,5 +35,14 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_variant(name, defines):
+    """Profiling / experiment builds: minlz_b200/libminlz_cuda_<name>.so with extra -D flags.
+    Loaded instead of the product library when MINLZ_CUDA_SO points at it (see _lib.py)."""
+    out = os.path.join(HERE, "libminlz_cuda_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out, os.path.join(CSRC, "mz_api.cu")])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

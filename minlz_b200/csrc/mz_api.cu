@@ -48,6 +48,7 @@ int fail(int code, const char *fmt, ...) {
 // ---- per-device state ------------------------------------------------------
 constexpr int kMaxDevices = 64;
 constexpr int kCounterSlots = 1024;
+constexpr int kDefaultL2Fetch = 0;  // bytes; 0 = leave the device default
 
 // Scratch for one encode launch: the per-warp match tables.  A slice may be
 // reused once the launch that used it has finished (event query).
@@ -105,6 +106,14 @@ int init_device(int device) {
     std::call_once(st.once, [&] {
         cudaError_t e = cudaSetDevice(device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) {
+            // The encoders probe 32-byte table slots at random: ask L2 to fetch 32 B per miss instead of
+            // promoting every miss to a wider DRAM read (a hint; MINLZ_CUDA_L2_FETCH=0 leaves it alone).
+            const char *g = getenv("MINLZ_CUDA_L2_FETCH");
+            const int gran = g ? atoi(g) : kDefaultL2Fetch;
+            if (gran > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran) != cudaSuccess)
+                cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaMalloc(&st.counters, kCounterSlots * sizeof(int));
         if (e == cudaSuccess) e = cudaMalloc(&st.crc_tabs, sizeof(mz::CrcTables));
         if (e == cudaSuccess) {
@@ -798,6 +807,16 @@ int mzcu_set_encoder_flavor(int flavor) {
 }
 
 int mzcu_get_encoder_flavor(void) { return g_flavor.load(std::memory_order_relaxed); }
+
+#ifdef MZ_ENC_STATS
+// profiling builds only (profiles/enc_stats.py): read and clear the walk counters
+extern "C" int mzcu_debug_enc_stats(unsigned long long *out) {
+    if (cudaMemcpyFromSymbol(out, mz::g_enc_stats, sizeof(mz::g_enc_stats)) != cudaSuccess) return MZCU_ERR_CUDA;
+    unsigned long long zero[16] = {0};
+    if (cudaMemcpyToSymbol(mz::g_enc_stats, zero, sizeof zero) != cudaSuccess) return MZCU_ERR_CUDA;
+    return MZCU_OK;
+}
+#endif
 const char *mzcu_last_error(void) { return g_err; }
 float mzcu_last_kernel_ms(void) { return g_last_kernel_ms; }
 

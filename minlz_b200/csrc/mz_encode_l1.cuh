@@ -191,6 +191,7 @@ __device__ __forceinline__ int emit_copy_lits3(uint8_t *dst, const uint8_t *lits
 template <bool kSmall>
 struct L1Params {
     static constexpr bool kAsm = false;
+    static constexpr bool kMayClamp = false;
     static constexpr int kMinMatch = 4;         // candidates are verified on 4 bytes
     static constexpr bool kBackExtend = true;   // :169-172
     __device__ __forceinline__ int table_bits() const { return kSmall ? 13 : 15; }
@@ -206,8 +207,10 @@ struct L1Params {
 
 // LevelFastest, Asm flavour, blocks > 512 KiB (encodeBlockAsm2MB / encodeBlockAsm:
 // gen.go:58-59: 15 bits, skipLog 6, hash6, step 4) -- the benchmark's class.
+template <bool kClamp>  // kClamp: the 8 MiB class (encodeBlockAsm), whose far candidates are clamped
 struct L1AsmBigParams {
     static constexpr bool kAsm = true;
+    static constexpr bool kMayClamp = kClamp;
     static constexpr int kMinMatch = 4;
     static constexpr bool kBackExtend = true;
     __device__ __forceinline__ int table_bits() const { return 15; }
@@ -227,6 +230,7 @@ struct L1AsmBigParams {
 template <bool kMatch8>
 struct AsmClassParams {
     static constexpr bool kAsm = true;
+    static constexpr bool kMayClamp = kMatch8;  // only the Fast dispatch sends blocks > 2 MiB here
     static constexpr int kMinMatch = kMatch8 ? 8 : 4;
     static constexpr bool kBackExtend = !kMatch8;
     int tb, sl, st, hb, ovh;
@@ -274,6 +278,7 @@ struct AsmClassParams {
 template <bool kSmall>
 struct L0Params {
     static constexpr bool kAsm = false;
+    static constexpr bool kMayClamp = false;
     static constexpr int kMinMatch = 8;
     static constexpr bool kBackExtend = false;  // encode_l0.go:164 `for false && ...`
     __device__ __forceinline__ int table_bits() const { return kSmall ? 12 : 13; }
@@ -315,7 +320,11 @@ constexpr int kSnapFwd = 24;  // forward bytes held in a slot
 // accesses (LDG.E.ENL2.256 / STG.E.ENL2.256): a single request per probe, and a
 // full-sector write per insert (no read-for-ownership of a half-written sector).
 __device__ __forceinline__ void slot_load(const Slot *p, uint4 &a, uint4 &b) {
-    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef MZ_SLOT_LD
+// no L1 allocation: a slot is read once per probe and 4.3 GB of tables never fit anyway (-2 %)
+#define MZ_SLOT_LD "ld.global.L1::no_allocate.v8.b32"
+#endif
+    asm volatile(MZ_SLOT_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(p)
                  : "memory");
@@ -386,6 +395,18 @@ struct SrcRing {
         for (int j = 0; j < 7; j++) out[j] = __funnelshift_r(w[j], w[j + 1], sh);
     }
 };
+
+// Optional walk counters for profiling builds (-DMZ_ENC_STATS, see profiles/enc_stats.py);
+// compiled out of the product library.
+#ifdef MZ_ENC_STATS
+__device__ unsigned long long g_enc_stats[16];
+#define ENC_STAT(i)                                         \
+    do {                                                    \
+        if (lane == 0) atomicAdd(&g_enc_stats[i], 1ull);    \
+    } while (0)
+#else
+#define ENC_STAT(i) ((void)0)
+#endif
 
 constexpr int kEncL1Warps = 4;  // warps per CTA
 #ifndef MZ_ENC_L1_MIN_CTAS
@@ -459,7 +480,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
     const int dstLimit = prm.dst_limit(n);
     // Asm flavour, 8 MiB class: far candidates are clamped (search) / rejected one byte earlier (re-match)
     constexpr int kClampDist = kMaxCopy3Offset - 2;  // gen.go:467-469: minPos = s - maxOffset + 2
-    const bool clamp_far = P::kAsm && n > (2 << 20);
+    const bool clamp_far = P::kAsm && P::kMayClamp && n > (2 << 20);
     const int fill_limit = (n + 64 + kRingChunk - 1) & ~(kRingChunk - 1);
     constexpr uint32_t kMinMask = P::kMinMatch == 8 ? 0xffu : 0xfu;
 
@@ -496,6 +517,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
     for (;;) {
         // ---------------- one round trip for the whole window ----------------
         const int wbase = rematch ? s - 2 : s;
+        ENC_STAT(0);
         // When the skip distance is long (incompressible data) only the first search
         // step can fall in the window: do not fetch slots nobody will consume.
         const int K = (!rematch && ((s - nextEmit) >> prm.skip_log()) >= 24) ? 8 : 32;
@@ -612,6 +634,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             const unsigned f = sm & ins_at & ((1u << L) - 1u);
             *fcand = -1;
             if (f == 0) return fast_hit;
+            ENC_STAT(6);
             *fcand = wbase + 31 - __clz(f);
             *fnz = probe_forwarded(ring_mem, wbase + L, *fcand);
             return (*fnz & kMinMask) == 0;
@@ -622,7 +645,10 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         auto match_end = [&](int base, int known, int f, int offset) -> int {
             int e = base + known;
             if (P::kAsm) {  // matchLen to the end of the block (gen.go:859-887)
-                if (f == kSnapFwd && e < n) e = extend_forward_exact(src, e, e - offset, n, lane, gate, slice);
+                if (f == kSnapFwd && e < n) {
+                    ENC_STAT(8);
+                    e = extend_forward_exact(src, e, e - offset, n, lane, gate, slice);
+                }
                 return min(e, n);
             }
             if (f == kSnapFwd || e > n - 8) {
@@ -647,7 +673,11 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                         break;
                     }
                     const int L = s - wbase;
-                    if (L >= K) break;
+                    if (L >= K) {
+                        ENC_STAT(3);
+                        break;
+                    }
+                    ENC_STAT(1);
                     int fcand = -1;
                     uint32_t fnz = 0;
                     bool hit = (ER >> L) & 1u;  // read before this step's inserts (:236-239)
@@ -690,16 +720,24 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                 done = true;
                 break;
             }
-            if (L + 2 >= K) break;
+            if (L + 2 >= K) {
+                ENC_STAT(4);
+                break;
+            }
             bool rhit;  // repeat check at t+1 (:94)
             if (rep_snap) {
                 const int dl = t + 1 - Rps;
-                if (dl > kSnapFwd - 4) break;  // not covered by the snapshot: next batch
+                if (dl > kSnapFwd - 4) {  // not covered by the snapshot: next batch
+                    ENC_STAT(5);
+                    break;
+                }
                 rhit = ((Rnz >> dl) & 0xfu) == 0;
             } else {
                 rhit = (Brep >> (L + 1)) & 1u;
             }
+            ENC_STAT(2);
             if (rhit) {
+                ENC_STAT(7);
                 ins |= 3u << L;
                 int base = t + 1;
                 // Go: both levels extend a repeat backwards; Asm: only with checkBack (gen.go:593)
@@ -776,7 +814,10 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             if (P::kBackExtend) {  // :169-172
                 const int room = min(mcand, mps - nextEmit);
                 int back = min(mbb, room);
-                if (back == 4 && room > 4) back += extend_backward(src, mcand - 4, mps - 4, nextEmit, lane);
+                if (back == 4 && room > 4) {
+                    ENC_STAT(9);
+                    back += extend_backward(src, mcand - 4, mps - 4, nextEmit, lane);
+                }
                 base = mps - back;
                 known = back + f;
             }
@@ -870,8 +911,10 @@ encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
         // encode_amd64.go:106,187: the smallest class needs len > 32 (Fast) / > 16
         if (n64 > (kSuperFast ? 32 : kMinNonLiteralBlockSize) && n64 <= kMaxBlockSize) {
             const int n = (int)n64;
-            if (!kSuperFast && n > (512 << 10))
-                res = encode_l1_block(L1AsmBigParams(), dp, sp, n, table, rings[warp], lane, gate, slice);
+            if (!kSuperFast && n > (2 << 20))
+                res = encode_l1_block(L1AsmBigParams<true>(), dp, sp, n, table, rings[warp], lane, gate, slice);
+            else if (!kSuperFast && n > (512 << 10))
+                res = encode_l1_block(L1AsmBigParams<false>(), dp, sp, n, table, rings[warp], lane, gate, slice);
             else
                 res = encode_l1_block(AsmClassParams<kSuperFast>::for_len(n), dp, sp, n, table, rings[warp], lane, gate,
                                       slice);
