@@ -39,6 +39,17 @@ func cudaErr(rc C.int) error {
 	}
 }
 
+// Encoder flavours: which of the reference's two builds the CUDA encoders mirror
+// byte for byte (minlz_cuda.h).  An amd64 deployment that wants the bytes it has
+// today calls SetEncoderFlavor(FlavorAMD64) once at start-up.
+const (
+	FlavorGo    = int(C.MZCU_FLAVOR_GO)    // encodeBlockGo / encodeBlockBetterGo / encodeFastBlockGo (noasm, purego)
+	FlavorAMD64 = int(C.MZCU_FLAVOR_AMD64) // encodeBlockAsm* / encodeBetterBlockAsm* / encodeFastBlockAsm*
+)
+
+// SetEncoderFlavor is process-wide, like the build tag it stands for.
+func SetEncoderFlavor(f int) error { return cudaErr(C.mzcu_set_encoder_flavor(C.int(f))) }
+
 func bptr(b []byte) *C.uint8_t {
 	if len(b) == 0 {
 		return nil

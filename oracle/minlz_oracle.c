@@ -1,10 +1,12 @@
 /*
- * minlz_oracle.c -- CPU restatement of the MinLZ block codec (pure-Go path).
+ * minlz_oracle.c -- CPU restatement of the MinLZ block codec: the pure-Go path
+ * and the amd64-assembly flavour of the encoders.
  *
  * TEST INFRASTRUCTURE ONLY: see minlz_oracle.h.  Every function cites the
  * reference file:line it follows (paths relative to the minio/minlz tree).
- * Encoder byte output: "parity unpinned" (no reference fixture pins it); the
- * decoder and the emitters are pinned by tests/test_oracle_golden.py.
+ * Pinned against the reference's own assembly run through oracle/_ref
+ * (tests/test_ref_asm.py) and against the reference's golden vectors
+ * (tests/test_oracle_golden.py).
  */
 #include "minlz_oracle.h"
 

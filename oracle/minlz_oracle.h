@@ -16,13 +16,19 @@
  *   wrappers  encode.go:74-139,168-244  decode.go:50-171  asm_none.go:51-76
  *   crc       minlz.go:133-140
  *
- * Pinning: decoder against testdata/Mark.Twain-Tom.Sawyer.txt.mzb -> .txt and
- * the emitters against TestEmitLiteral / TestEmitCopy (minlz_test.go:871-1026);
- * see tests/test_oracle_golden.py.  The L1/L2 encoders' exact output bytes are
- * NOT pinned by any reference fixture ("parity unpinned" for encoder bytes):
- * the reference has no Go toolchain-free way to run here and no test that
- * fixes encoder output.  Their fidelity rests on line-by-line restatement,
- * round-trip through the pinned decoder, and size sanity.
+ *   amd64     _generate/gen.go:257-1155 (genEncodeBlockAsm), :1171-2038
+ *   flavour   (genEncodeBetterBlockAsm), class tables gen.go:57-88,
+ *             dispatch encode_amd64.go:37-271
+ *
+ * Pinning: PINNED against the reference itself.  oracle/_ref (p9_to_gas.py +
+ * ref_shim.c) runs the reference's own asm_amd64.s here; tests/test_ref_asm.py
+ * requires the decoder, the emitters, matchLen and the amd64-flavour encoders
+ * (all levels, every size class) to agree with it byte for byte.  The decoder is
+ * also pinned to testdata/Mark.Twain-Tom.Sawyer.txt.mzb -> .txt and the emitters
+ * to TestEmitLiteral / TestEmitCopy (minlz_test.go:871-1026).  The Go-flavour
+ * encoders (Go source, nothing to run here) are anchored through the real
+ * decoder and through the tail-only difference to the assembly for blocks
+ * > 512 KiB.
  */
 #ifndef MINLZ_ORACLE_H
 #define MINLZ_ORACLE_H
