@@ -442,6 +442,114 @@ __device__ __noinline__ uint32_t probe_forwarded(const uint32_t *ring_mem, int p
     return nzmask24(B + 1, A + 1) | bb << 24;
 }
 
+// ---- token writer ---------------------------------------------------------------
+// The walk appends its matches (base, end, offset | kind << 24) to a small per-warp
+// record ring in shared memory; whenever 32 are pending they are turned into tokens
+// TOGETHER: lane = record.  Every lane builds its token bytes (literal header, copy /
+// repeat / fused token, trailing repeat), one warp prefix sum gives the output
+// positions, the reference's bail-out tests are evaluated per lane with the same
+// values of d the serial code would see, and the bytes leave with a fixed number of
+// predicated stores.  ~9 warp instructions per token instead of ~95 for a serial
+// token-at-a-time writer, and the work moves out of the walk's dependency chain.
+constexpr int kRecRing = 64;  // records per warp (>= 31 pending + 9 new per batch)
+
+#ifndef MZ_ENC_GROUP_EMIT
+#define MZ_ENC_GROUP_EMIT 1
+#endif
+
+// Emits `cnt` (1..32) records held one per lane.  Returns false when a bail-out test fires.
+template <class P>
+__device__ __forceinline__ bool emit_group(const P prm, uint8_t *dst, const uint8_t *src, int &d, int &emitted,
+                                           const int base, const int rk, const int end, const int cnt, const int lane,
+                                           const int sLimit, const int dstLimit) {
+    const bool valid = lane < cnt;
+    const int prev_end = __shfl_up_sync(kFullMask, end, 1);
+    const int ne = lane == 0 ? emitted : prev_end;  // literals start where the previous record ended
+    const int kind = rk >> 24, rep = rk & 0xffffff;  // kind 3: literals + repeat, 0: (literals +) copy
+    const int litLen = valid ? base - ne : 0;
+    const int length = end - base;
+    bool sep = false, fused2 = false, fused3 = false;  // how the literals travel (:190-206)
+    if (valid && litLen > 0) {
+        if (kind || litLen > prm.max_fuse_lits() || rep < kMinCopy2Offset) sep = true;
+        else if (rep <= kMaxCopy2Offset) fused2 = true;
+        else fused3 = true;
+    }
+    uint64_t lh = 0, tok = 0, post = 0;
+    int n_lh = 0, n_tok = 0, n_post = 0;
+    if (sep) {
+        lh = tok_literal_hdr((uint32_t)litLen, &n_lh);
+        if (prm.lit_quirk() && n_lh == 3) {  // gen.go:2193-2200
+            n_lh = 4;
+            lh = (lh & ~0xffull) | (31u << 3 | kTagLiteral);
+        }
+    }
+    if (valid) {
+        if (kind) {
+            tok = tok_repeat((uint32_t)length, &n_tok);
+        } else if (fused2) {
+            tok = tok_copy2_fused((uint32_t)rep, (uint32_t)length, (uint32_t)litLen, &post, &n_post);
+            n_tok = 3;
+        } else if (fused3) {
+            tok = tok_copy3((uint32_t)rep, (uint32_t)length, (uint32_t)litLen, &n_tok);
+        } else {
+            tok = tok_copy((uint32_t)rep, (uint32_t)length, &n_tok);
+        }
+    }
+    const int total = n_lh + n_tok + n_post + litLen;
+    int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int d0 = d + incl - total;  // d when the serial code reaches this record
+
+    bool fail = false;
+    if (valid) {
+        const int ovh = prm.lit_overhead();
+        if (kind) {  // :103; Asm: gen.go:614-624 checkDst(litLen)
+            fail = P::kAsm ? d0 + litLen + ovh >= dstLimit : d0 + litLen > dstLimit;
+        } else {
+            if (P::kAsm && d0 >= dstLimit) fail = true;  // gen.go:828 (and :1039 with the same d)
+            if (sep && (P::kAsm ? d0 + litLen + ovh >= dstLimit : d0 + (end - ne) > dstLimit)) fail = true;  // :194
+            // :229, first thing the re-match loop does; Asm: gen.go:955-975
+            if (end < sLimit && (P::kAsm ? d0 + total >= dstLimit : d0 + total > dstLimit)) fail = true;
+        }
+    }
+    if (__any_sync(kFullMask, fail)) return false;
+
+    uint8_t *o = dst + d0;
+    const int pos_tok = sep ? n_lh + litLen : 0;
+    const int pos_post = n_tok + litLen;  // fused2 only
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < n_lh) o[k] = (uint8_t)(lh >> (8 * k));
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+        if (k < n_tok) o[pos_tok + k] = (uint8_t)(tok >> (8 * k));
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < n_post) o[pos_post + k] = (uint8_t)(post >> (8 * k));
+    if (fused2 || fused3) {  // <= 4 literals right behind the copy header
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < litLen) o[n_tok + k] = src[ne + k];
+    }
+    // separate literal runs are copied by the whole warp, one run after the other
+    unsigned m = __ballot_sync(kFullMask, sep);
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int s_ne = __shfl_sync(kFullMask, ne, j);
+        const int s_len = __shfl_sync(kFullMask, litLen, j);
+        const int s_pos = __shfl_sync(kFullMask, d0 + n_lh, j);
+        copy_bytes(dst + s_pos, src + s_ne, s_len, lane);
+    }
+    d += __shfl_sync(kFullMask, incl, 31);
+    emitted = __shfl_sync(kFullMask, end, cnt - 1);
+    return true;
+}
+
 // Cold path of the Asm flavour's 8 MiB class: a far candidate is clamped to
 // s - 2162685 (gen.go:466-490) and matched THERE; the slot snapshot is of another
 // position, so compare straight from the source.  Same result layout as above.
@@ -510,6 +618,10 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
     int q_base = 0, q_rep = 0, q_end = 0;  // q_rep = offset | kind << 24
     int q_cnt = 0;
     int emitted = 0;  // nextEmit as the token writer sees it
+#if MZ_ENC_GROUP_EMIT
+    uint32_t *recs = ring_mem + kRingWords + kRingMirror;  // [3][kRecRing]: base, offset | kind << 24, end
+    int r_head = 0, r_pending = 0;
+#endif
 
     const unsigned below = (1u << lane) - 1u;
     const unsigned above = ~((2u << lane) - 1u);
@@ -542,7 +654,26 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             }
         }
 
-        // ---------------- the loads are in flight: write the queued tokens ----------------
+        // ---------------- the loads are in flight: write queued tokens ----------------
+#if MZ_ENC_GROUP_EMIT
+        if (lane < q_cnt) {
+            const int w = (r_head + r_pending + lane) & (kRecRing - 1);
+            recs[w] = (uint32_t)q_base;
+            recs[kRecRing + w] = (uint32_t)q_rep;
+            recs[2 * kRecRing + w] = (uint32_t)q_end;
+        }
+        r_pending += q_cnt;
+        __syncwarp();
+        while (r_pending >= 32 || (done && r_pending > 0)) {
+            const int cnt = min(r_pending, 32);
+            const int r = (r_head + lane) & (kRecRing - 1);
+            const int g_base = (int)recs[r], g_rk = (int)recs[kRecRing + r], g_end = (int)recs[2 * kRecRing + r];
+            if (!emit_group(prm, dst, src, d, emitted, g_base, g_rk, g_end, cnt, lane, sLimit, dstLimit)) return 0;
+            r_head = (r_head + cnt) & (kRecRing - 1);
+            r_pending -= cnt;
+        }
+        __syncwarp();
+#else
         for (int i = 0; i < q_cnt; i++) {
             const int base = __shfl_sync(kFullMask, q_base, i);
             const int rk = __shfl_sync(kFullMask, q_rep, i);
@@ -574,6 +705,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             // :229, first thing the re-match loop does; Asm: gen.go:955-975
             if (end < sLimit && (P::kAsm ? d >= dstLimit : d > dstLimit)) return 0;
         }
+#endif
         q_cnt = 0;
         if (done) break;
 
@@ -858,7 +990,7 @@ __global__ void __launch_bounds__(kEncL1Warps * 32, MZ_ENC_L1_MIN_CTAS)
 encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                  uint32_t *__restrict__ out_len, int *counter, Slot *tables, const int *gate, int slice) {
-    __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror];
+    __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror + 3 * kRecRing];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
@@ -894,7 +1026,7 @@ __global__ void __launch_bounds__(kEncL1Warps * 32, MZ_ENC_L1_MIN_CTAS)
 encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                      const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                      uint32_t *__restrict__ out_len, int *counter, Slot *tables, const int *gate, int slice) {
-    __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror];
+    __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror + 3 * kRecRing];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * kEncL1Warps + warp;

@@ -1,3 +1,4 @@
 O=gpurun_out; mkdir -p $O
-for v in "" _cg _na; do echo "== variant '$v'"; MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda$v.so timeout 300 python profiles/ab_encode.py 1 4096 1048576 json 3 2>&1 | tail -2; done | tee $O/slotld.log
-for v in "" _cg _na; do echo "== ncu variant '$v'"; MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda$v.so timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_read.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum,gpu__time_duration.sum --clock-control none -k regex:encode_l1 -c 1 python profiles/prof_run.py 1024 2>&1 | grep -E "dram__|lts__|l1tex|gpu__time"; done | tee -a $O/slotld.log
+timeout 900 python -m pytest tests -m gpu -x -q > $O/t8.log 2>&1; tail -15 $O/t8.log
+for v in "" _serial; do echo "== variant '$v'"; MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda$v.so timeout 300 python profiles/ab_encode.py 1 4096 1048576 json 3 2>&1 | tail -2; done | tee $O/group.log
+MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda.so timeout 300 python profiles/ab_encode.py -1 4096 1048576 json 3 2>&1 | tail -2 | tee -a $O/group.log
