@@ -638,7 +638,8 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         uint32_t W[7];  // src[p-4 .. p+24)
         uint32_t h = 0;
         uint4 ea = make_uint4(0, 0, 0, 0), eb = ea;
-        uint32_t rep4 = 0;
+        uint32_t rep_lo = 0, rep_hi = 0;  // raw words around src[p - repeat]; shifted together after the shadow work
+        unsigned rep_sh = 0;
         uint64_t far8 = 0;  // src[p-kClampDist-2 .. +8): the three clamped candidates of this position
         const bool rep_lane = active && p >= repeat;
         if (!done) {
@@ -647,7 +648,14 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             ring.fetch28(p - 4, W);
             h = prm.hash((uint64_t)W[2] << 32 | W[1]);
             if (active) slot_load(table + h, ea, eb);
-            if (rep_lane) rep4 = ldg_u32_unaligned(src + p - repeat);
+            if (rep_lane) {
+                // (the funnel shift would wait for the load right here: keep the raw words)
+                const uintptr_t ra = reinterpret_cast<uintptr_t>(src + p - repeat);
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(ra & ~uintptr_t(3));
+                rep_sh = (unsigned)(ra & 3) * 8;
+                rep_lo = rw[0];
+                if (rep_sh) rep_hi = rw[1];
+            }
             if (clamp_far && active && p >= kClampDist) {
                 const int lo = p - kClampDist - 2;
                 far8 = lo >= 0 ? ldg_u64_unaligned(src + lo) : ldg_u64_unaligned(src) << (8 * -lo);
@@ -751,6 +759,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             }
             ER = E0;
         }
+        const uint32_t rep4 = __funnelshift_r(rep_lo, rep_hi, rep_sh);
         const unsigned Brep = __ballot_sync(kFullMask, rep_lane && rep4 == W[1]);
 
         // ---------------- replay the serial walk over the window ----------------

@@ -14,6 +14,8 @@ nblk = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 bs = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 kind = sys.argv[3] if len(sys.argv) > 3 else "json"
 passes = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+# the flavour bench.py runs by default: the reference's amd64 assembly (MINLZ_FLAVOR=go for the other one)
+mz.set_encoder_flavor(mz.FlavorGo if os.environ.get("MINLZ_FLAVOR") == "go" else mz.FlavorAMD64)
 dev = torch.device("cuda:0")
 src = synth.make_blocks(kind, nblk, bs, device=dev).reshape(-1)
 soff = torch.arange(nblk + 1, dtype=torch.int64, device=dev) * bs
