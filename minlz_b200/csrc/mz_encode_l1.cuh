@@ -613,10 +613,14 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
     bool rematch = false;  // the cursor is in the re-match loop (:222-265)
     bool done = false;     // reached emitRemainder
 
-    // queue of this batch's matches, entry i in lane i: [base, end) at offset rep
-    // (the literals of an entry start where the previous entry ended: emitted)
-    int q_base = 0, q_rep = 0, q_end = 0;  // q_rep = offset | kind << 24
+    // A match found in this batch belongs to the lane of the position it was probed at
+    // (positions only grow within a batch, so lane order = stream order): the owner lane
+    // holds [o_base, o_end) and o_rep = offset | kind << 24; `mmask` marks the owners.
+    // (the literals of a match start where the previous one ended: emitted)
+#if !MZ_ENC_GROUP_EMIT
+    int q_base = 0, q_rep = 0, q_end = 0;
     int q_cnt = 0;
+#endif
     int emitted = 0;  // nextEmit as the token writer sees it
 #if MZ_ENC_GROUP_EMIT
     uint32_t *recs = ring_mem + kRingWords + kRingMirror;  // [3][kRecRing]: base, offset | kind << 24, end
@@ -632,7 +636,10 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         ENC_STAT(0);
         // When the skip distance is long (incompressible data) only the first search
         // step can fall in the window: do not fetch slots nobody will consume.
-        const int K = (!rematch && ((s - nextEmit) >> prm.skip_log()) >= 24) ? 8 : 32;
+#ifndef MZ_ENC_WINDOW
+#define MZ_ENC_WINDOW 32  // positions probed per round trip (each probe costs a 128-byte DRAM line)
+#endif
+        const int K = (!rematch && ((s - nextEmit) >> prm.skip_log()) >= 24) ? 8 : MZ_ENC_WINDOW;
         const int p = wbase + lane;
         const bool active = lane < K && !done;
         uint32_t W[7];  // src[p-4 .. p+24)
@@ -664,14 +671,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
 
         // ---------------- the loads are in flight: write queued tokens ----------------
 #if MZ_ENC_GROUP_EMIT
-        if (lane < q_cnt) {
-            const int w = (r_head + r_pending + lane) & (kRecRing - 1);
-            recs[w] = (uint32_t)q_base;
-            recs[kRecRing + w] = (uint32_t)q_rep;
-            recs[2 * kRecRing + w] = (uint32_t)q_end;
-        }
-        r_pending += q_cnt;
-        __syncwarp();
         while (r_pending >= 32 || (done && r_pending > 0)) {
             const int cnt = min(r_pending, 32);
             const int r = (r_head + lane) & (kRecRing - 1);
@@ -713,8 +712,8 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             // :229, first thing the re-match loop does; Asm: gen.go:955-975
             if (end < sLimit && (P::kAsm ? d >= dstLimit : d > dstLimit)) return 0;
         }
-#endif
         q_cnt = 0;
+#endif
         if (done) break;
 
         const unsigned same = __match_any_sync(kFullMask, h);
@@ -767,6 +766,29 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         int rep_snap = 0;     // repeat checks come from the last match's snapshot (Rnz, Rps)
         uint32_t Rnz = 0;
         int Rps = 0;
+#if MZ_ENC_GROUP_EMIT
+        // Every lane prepares the record of "a re-match hit at my position" up front: the match
+        // starts at p (no literals, no backward extension in the re-match loop), runs for the
+        // f_own equal snapshot bytes and has offset p - cand.  The replay then only needs the
+        // end of such a match (one shuffle) to move on.  Lanes whose answer needs more than the
+        // snapshot -- a forwarded probe, a match of 24+ bytes, the block's tail -- are `cold`
+        // and take the general path, which overwrites the owner lane's record.
+        uint32_t o_nz = nz & 0xffffffu;
+        const int f_own = o_nz ? __ffs(o_nz) - 1 : kSnapFwd;
+        int o_base = p, o_rep = dist, o_end = P::kAsm ? min(p + f_own, n) : p + f_own;
+        const unsigned cold = dup | __ballot_sync(kFullMask, f_own == kSnapFwd || (!P::kAsm && p + f_own > n - 8));
+        unsigned mmask = 0;   // owner lanes of this batch's matches
+        int Rlane = -1;       // owner lane of the last fast re-match (its Rnz / repeat are fetched on demand)
+        auto settle = [&]() {  // make Rnz / Rps / repeat current after fast re-matches
+            if (Rlane >= 0) {
+                Rnz = __shfl_sync(kFullMask, o_nz, Rlane);
+                repeat = __shfl_sync(kFullMask, o_rep, Rlane);
+                Rps = wbase + Rlane;
+                rep_snap = 1;
+                Rlane = -1;
+            }
+        };
+#endif
 
         // Probe of lane L against the table as of `ins_at`: hit flag; when the slot was
         // written earlier in this batch the candidate is that insert (*fcand, *fnz).
@@ -819,6 +841,21 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                         break;
                     }
                     ENC_STAT(1);
+#if MZ_ENC_GROUP_EMIT
+                    if (!((cold >> L) & 1u)) {  // fast: everything this step needs is already in lane L
+                        ins |= 5u << (L - 2);
+                        if (!((ER >> L) & 1u)) {
+                            rematch = false;
+                            s++;
+                            break;
+                        }
+                        mmask |= 1u << L;
+                        Rlane = L;
+                        s = __shfl_sync(kFullMask, o_end, L);
+                        continue;
+                    }
+                    settle();
+#endif
                     int fcand = -1;
                     uint32_t fnz = 0;
                     bool hit = (ER >> L) & 1u;  // read before this step's inserts (:236-239)
@@ -839,12 +876,17 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                     const int f = mnz ? __ffs(mnz) - 1 : kSnapFwd;
                     repeat = s - mcand;
                     const int e = match_end(s, f, f, repeat);
+#if MZ_ENC_GROUP_EMIT
+                    if (lane == L) o_base = s, o_rep = repeat, o_end = e;
+                    mmask |= 1u << L;
+#else
                     if (lane == q_cnt) {
                         q_base = s;
                         q_rep = repeat;
                         q_end = e;
                     }
                     q_cnt++;
+#endif
                     rep_snap = 1;
                     Rnz = mnz;
                     Rps = s;
@@ -854,6 +896,9 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             }
 
             // ---- one search step at t (:70-160) ----
+#if MZ_ENC_GROUP_EMIT
+            settle();
+#endif
             const int t = s;
             const int L = t - wbase;
             const int nextS = t + ((t - nextEmit) >> prm.skip_log()) + prm.step();  // :79
@@ -885,12 +930,17 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                 if (!P::kAsm || P::kBackExtend) base -= extend_backward(src, base - repeat, base, nextEmit, lane);
                 s = P::kAsm ? extend_forward_exact(src, t + 5, t + 5 - repeat, n, lane, gate, slice)  // gen.go:632-660
                             : extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane, gate, slice);
+#if MZ_ENC_GROUP_EMIT
+                if (lane == L + 1) o_base = base, o_rep = repeat | 3 << 24, o_end = s;  // probed at t+1
+                mmask |= 2u << L;
+#else
                 if (lane == q_cnt) {
                     q_base = base;
                     q_rep = repeat | 3 << 24;
                     q_end = s;
                 }
                 q_cnt++;
+#endif
                 nextEmit = s;
                 if (s >= sLimit) {
                     done = true;
@@ -964,12 +1014,17 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             }
             repeat = mps - mcand;
             const int e = match_end(base, known, f, repeat);
+#if MZ_ENC_GROUP_EMIT
+            if (lane == mps - wbase) o_base = base, o_rep = repeat, o_end = e;
+            mmask |= 1u << (mps - wbase);
+#else
             if (lane == q_cnt) {
                 q_base = base;
                 q_rep = repeat;
                 q_end = e;
             }
             q_cnt++;
+#endif
             rep_snap = 1;
             Rnz = mnz;
             Rps = mps;
@@ -977,6 +1032,18 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             rematch = true;
         }
 
+#if MZ_ENC_GROUP_EMIT
+        settle();  // `repeat` feeds the next batch's repeat-check loads
+        if (mmask) {  // append this batch's matches to the record ring, in lane (= stream) order
+            if ((mmask >> lane) & 1u) {
+                const int w = (r_head + r_pending + __popc(mmask & below)) & (kRecRing - 1);
+                recs[w] = (uint32_t)o_base;
+                recs[kRecRing + w] = (uint32_t)o_rep;
+                recs[2 * kRecRing + w] = (uint32_t)o_end;
+            }
+            r_pending += __popc(mmask);
+        }
+#endif
         // ---------------- write back the inserts the replay performed ----------------
         if (((ins >> lane) & 1u) && (same & ins & above) == 0) {  // a later insert on the same slot wins
             slot_store(table + h, make_uint4((uint32_t)p, W[0], W[1], W[2]), make_uint4(W[3], W[4], W[5], W[6]));
