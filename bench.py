@@ -398,6 +398,13 @@ def main():
             "traffic": enc_traffic if dominant_is_enc else ncu_traffic("decode"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": enc_bytes if dominant_is_enc else dec_bytes,
             "share_of_step": round((enc_ms if dominant_is_enc else dec_ms) / total_ms, 4)}
+    if roof["traffic"]:
+        # what the kernel actually moves: table probes are random 32-byte reads and the B200 L2 fetches a
+        # whole 128-byte line per miss (profiles/r01_micro_gather32.txt: 4.7 TB/s ceiling for such gathers)
+        t_ms = (enc_ms if dominant_is_enc else dec_ms) / K
+        roof["traffic_gbs"] = round(roof["traffic"] / (t_ms * 1e-3) / 1e9, 1)
+        roof["traffic_frac_of_peak"] = round(roof["traffic_gbs"] / peak, 4)
+        roof["random_line_gather_ceiling_gbs"] = 4700.0
     roof_dec = {"bound": "hbm", "kernel": "decode_pc_kernel", "achieved": round(dec_gbs, 3), "peak": peak, "unit": "GB/s",
                 "frac": round(dec_gbs / peak, 5), "traffic": ncu_traffic("decode"),
                 "algorithmic_bytes_per_launch": dec_bytes, "share_of_step": round(dec_ms / total_ms, 4)}

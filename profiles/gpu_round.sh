@@ -13,3 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:encode_l1 -c 1 -o $O/enc_l1_full -f python profiles/prof_run.py 4096 > $O/ncu_enc.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode_pc -c 1 -o $O/dec_pc_full -f python profiles/prof_run.py 4096 > $O/ncu_dec.log 2>&1
 tail -3 $O/pytest_gpu.log; cat $O/bench_default.json $O/bench_reference.json
+for lv in -1 1 2; do timeout 300 python profiles/ab_encode.py $lv 4096 1048576 json 3 2>&1 | tail -2; done | tee $O/ab_levels.log
+MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda_stats.so timeout 300 python profiles/enc_stats.py 1 512 json > $O/enc_stats.log 2>&1
