@@ -23,14 +23,7 @@ func encodeOne(dst, src []byte, level int) int {
 func encodeBlock(dst, src []byte) (d int)       { return encodeOne(dst, src, LevelFastest) }
 func encodeBlockBetter(dst, src []byte) (d int) { return encodeOne(dst, src, LevelBalanced) }
 
-// LevelSuperFast and LevelSmallest are not on the accelerated path; they keep
-// the pure-Go implementations (encode_l0.go, encode_l3.go).
-func encodeBlockFast(dst, src []byte) (d int) {
-	if len(src) < minNonLiteralBlockSize {
-		return 0
-	}
-	if len(src) <= 65536 {
-		return encodeFastBlockGo64K(dst, src)
-	}
-	return encodeFastBlockGo(dst, src)
-}
+func encodeBlockFast(dst, src []byte) (d int)   { return encodeOne(dst, src, LevelSuperFast) }
+
+// LevelSmallest is not on the accelerated path; it keeps the pure-Go
+// implementation (encode_l3.go).

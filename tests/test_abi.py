@@ -28,6 +28,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.mzcu_abi_version() == 1
 
 
+def test_encoder_flavour_setting():
+    # include/minlz_cuda.h: process-wide, Go flavour by default, unknown values refused
+    assert minlz_b200.get_encoder_flavor() == minlz_b200.FlavorGo
+    minlz_b200.set_encoder_flavor(minlz_b200.FlavorAMD64)
+    assert minlz_b200.get_encoder_flavor() == minlz_b200.FlavorAMD64
+    minlz_b200.set_encoder_flavor(minlz_b200.FlavorGo)
+    with pytest.raises(Exception):
+        minlz_b200.set_encoder_flavor(7)
+    assert minlz_b200.get_encoder_flavor() == minlz_b200.FlavorGo
+
+
 def test_max_encoded_len():
     # minlz_test.go:42-69 TestMaxEncodedLen / encode.go:234-244
     assert minlz_b200.MaxEncodedLen(0) == 1
