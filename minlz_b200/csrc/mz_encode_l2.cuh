@@ -8,11 +8,18 @@
 // s+1), same skip rule, same re-indexing of the match interior.
 //
 // Mapping: one block per warp, all blocks of the batch in flight at once; the
-// 576 KiB of tables per block do not fit shared memory (and shared memory
-// would cap the chip at ~148 chains of a latency-bound walk), so they live in
-// a global-memory workspace slice per warp.  Lanes 0-3 issue the independent
-// probes of a step (long, short, repeat, long at s+1) in one round trip; match
-// extension is lane parallel.
+// tables do not fit shared memory (and shared memory would cap the chip at ~148
+// chains of a latency-bound walk), so they live in a global-memory workspace slice
+// per warp.  Lanes 0-3 issue the independent probes of a step (long, short, repeat,
+// long at s+1) in one round trip; match extension is lane parallel.
+//
+// Table entries are SNAPSHOTS, as in the L1 kernel: a long-table entry is
+// {position, the 8 source bytes at it} (16 B), a short-table entry {position, 4
+// bytes} (8 B).  The reference's table -> src[candidate] chain (two dependent DRAM
+// round trips per step) becomes one; the bytes are copies of immutable source
+// bytes, so every decision is unchanged.  An untouched (zero) entry stands for
+// candidate 0, whose bytes are src[0..8) (encode_l2.go:84,121-130).  2.1 MiB of
+// workspace per in-flight block.
 #pragma once
 
 #include "mz_common.cuh"
@@ -29,7 +36,15 @@ struct L2Params {
 };
 
 constexpr int kEncL2Warps = 4;
-constexpr size_t kEncL2WsBytesPerWarp = ((size_t)(1 << 17) + (1 << 14)) * 4;  // 576 KiB
+constexpr size_t kEncL2WsBytesPerWarp = ((size_t)(1 << 17) * 16) + ((size_t)(1 << 14) * 8);  // 2 MiB + 128 KiB
+
+// long-table entry {pos, 8 bytes at pos}; short-table entry {pos, 4 bytes at pos}
+__device__ __forceinline__ void l2_put_long(uint4 *t, uint32_t h, int pos, uint64_t bytes) {
+    t[h] = make_uint4((uint32_t)pos, (uint32_t)bytes, (uint32_t)(bytes >> 32), 0u);
+}
+__device__ __forceinline__ void l2_put_short(uint2 *t, uint32_t h, int pos, uint64_t bytes) {
+    t[h] = make_uint2((uint32_t)pos, (uint32_t)bytes);
+}
 
 // 8 bytes at pos, zero filled past n; never touches a word with no byte < n.
 __device__ __forceinline__ uint64_t ld64_clamped(const uint8_t *src, int pos, int n) {
@@ -73,9 +88,10 @@ __device__ __forceinline__ int extend_to_end(const uint8_t *src, int n, int s, i
 }
 
 template <bool kSmall>
-__device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, uint32_t *lTable, uint32_t *sTable,
+__device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, uint4 *lTable, uint2 *sTable,
                                const int lane) {
     using P = L2Params<kSmall>;
+    const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
     const int sLimit = n - kInputMargin;
     const int dstLimit = n - (n >> 5) - 6;
     int nextEmit = 0;
@@ -99,16 +115,23 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
             if (lane == 1) h = P::hashS(cv);
             if (lane == 3) h = P::hashL(cv >> 8);
             const uint32_t hL = __shfl_sync(kFullMask, h, 0);
-            if (lane == 0 || lane == 3) c = (int)lTable[h];
-            if (lane == 1) c = (int)sTable[h];
-            if (lane == 3 && h == hL) c = s;  // lTable[hashL] = s precedes the s+1 probe (:124, :207)
-            __syncwarp();
-            if (lane == 0) lTable[h] = (uint32_t)s;
-            if (lane == 1) sTable[h] = (uint32_t)s;
-            uint64_t v = 0;
-            if (lane < 2) v = ldg_u64_unaligned(src + c);                 // valLong / valShort (:127-128)
+            uint64_t v = 0;  // the candidate's bytes: valLong / valShort (:127-128), load32 (:209)
+            if (lane == 0 || lane == 3) {
+                const uint4 e = lTable[h];
+                c = (int)e.x;
+                v = (uint64_t)e.z << 32 | e.y;
+            }
+            if (lane == 1) {
+                const uint2 e = sTable[h];
+                c = (int)e.x;
+                v = e.y;
+            }
             if (lane == 2) v = ldg_u64_unaligned(src + s - repeat);       // :139
-            if (lane == 3) v = ldg_u32_unaligned(src + c);                // :209
+            if (lane != 2 && c == 0) v = src0;
+            if (lane == 3 && h == hL) c = s, v = cv;  // lTable[hashL] = s precedes the s+1 probe (:124, :207)
+            __syncwarp();
+            if (lane == 0) l2_put_long(lTable, h, s, cv);
+            if (lane == 1) l2_put_short(sTable, h, s, cv);
             const uint64_t repeatMask = 0xffffffffull << 8;
             bool f8 = false, f4 = false;
             if (lane == 0) {
@@ -145,10 +168,10 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
                     const uint64_t cv0 = ldg_u64_unaligned(src + index0);
                     const uint64_t cv1 = ldg_u64_unaligned(src + index1);
                     if (lane == 0) {
-                        lTable[P::hashL(cv0)] = (uint32_t)index0;
-                        sTable[P::hashS(cv0 >> 8)] = (uint32_t)(index0 + 1);
-                        lTable[P::hashL(cv1)] = (uint32_t)index1;
-                        sTable[P::hashS(cv1 >> 8)] = (uint32_t)(index1 + 1);
+                        l2_put_long(lTable, P::hashL(cv0), index0, cv0);
+                        l2_put_short(sTable, P::hashS(cv0 >> 8), index0 + 1, cv0 >> 8);
+                        l2_put_long(lTable, P::hashL(cv1), index1, cv1);
+                        l2_put_short(sTable, P::hashS(cv1 >> 8), index1 + 1, cv1 >> 8);
                     }
                     index0 += 2;
                     index1 -= 2;
@@ -162,7 +185,7 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
                 break;
             }
             if (m4 & 2u) {  // short candidate (:204-216): try the long table at s+1
-                if (lane == 3) lTable[h] = (uint32_t)(s + 1);
+                if (lane == 3) l2_put_long(lTable, h, s + 1, ldg_u64_unaligned(src + s + 1));
                 __syncwarp();
                 if (m4 & 8u) {
                     candidateL = __shfl_sync(kFullMask, c, 3);
@@ -225,10 +248,10 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
                 const uint64_t cv0 = ldg_u64_unaligned(src + index0);
                 const uint64_t cv1 = ldg_u64_unaligned(src + index1);
                 if (lane == 0) {
-                    lTable[P::hashL(cv0)] = (uint32_t)index0;
-                    sTable[P::hashS(cv0 >> 8)] = (uint32_t)(index0 + 1);
-                    lTable[P::hashL(cv1)] = (uint32_t)index1;
-                    sTable[P::hashS(cv1 >> 8)] = (uint32_t)(index1 + 1);
+                    l2_put_long(lTable, P::hashL(cv0), index0, cv0);
+                    l2_put_short(sTable, P::hashS(cv0 >> 8), index0 + 1, cv0 >> 8);
+                    l2_put_long(lTable, P::hashL(cv1), index1, cv1);
+                    l2_put_short(sTable, P::hashS(cv1 >> 8), index1 + 1, cv1 >> 8);
                 }
                 index0 += 1;
                 index1 -= 1;
@@ -239,8 +262,8 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
                     const uint64_t a = ldg_u64_unaligned(src + index0);
                     const uint64_t b = ldg_u64_unaligned(src + index2);
                     if (lane == 0) {
-                        lTable[P::hashL(a)] = (uint32_t)index0;
-                        lTable[P::hashL(b)] = (uint32_t)index2;
+                        l2_put_long(lTable, P::hashL(a), index0, a);
+                        l2_put_long(lTable, P::hashL(b), index2, b);
                     }
                     index0 += 2;
                     index2 += 2;
@@ -298,7 +321,8 @@ struct BetterAsmClass {
 };
 
 __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const uint8_t *src, const int n,
-                                   uint32_t *lTable, uint32_t *sTable, const int lane) {
+                                   uint4 *lTable, uint2 *sTable, const int lane) {
+    const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
     const int sLimit = n - P.inMargin;                    // gen.go:1272-1282
     const int dstLimit = n - P.outMargin - (n >> 5);      // gen.go:1284-1297
     int nextEmit = 0;
@@ -320,17 +344,27 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
         if (lane == 1) h = P.hashS(cv);
         if (lane == 3) h = P.hashL(cv >> 8);
         const uint32_t hL = __shfl_sync(kFullMask, h, 0);
-        if (lane == 0 || lane == 3) c = (int)lTable[h];
-        if (lane == 1) c = (int)sTable[h];
-        if (lane == 3 && h == hL) c = s;  // lTab[hash0] = s is stored before the s+1 probe reads
-        __syncwarp();
-        if (lane == 0) lTable[h] = (uint32_t)s;
-        if (lane == 1) sTable[h] = (uint32_t)s;
-        if (P.clamp && c <= minPos) c = minPos;  // CMOVLLE: compared (and matched) at the clamped position
-        uint64_t v = 0;
-        if (lane < 2) v = ldg_u64_unaligned(src + c);
+        uint64_t v = 0;  // the candidate's bytes
+        if (lane == 0 || lane == 3) {
+            const uint4 e = lTable[h];
+            c = (int)e.x;
+            v = (uint64_t)e.z << 32 | e.y;
+        }
+        if (lane == 1) {
+            const uint2 e = sTable[h];
+            c = (int)e.x;
+            v = e.y;
+        }
         if (lane == 2) v = ldg_u64_unaligned(src + s - repeat);
-        if (lane == 3) v = ldg_u32_unaligned(src + c);
+        if (lane != 2 && c == 0) v = src0;
+        if (lane == 3 && h == hL) c = s, v = cv;  // lTab[hash0] = s is stored before the s+1 probe reads
+        __syncwarp();
+        if (lane == 0) l2_put_long(lTable, h, s, cv);
+        if (lane == 1) l2_put_short(sTable, h, s, cv);
+        if (P.clamp && lane != 2 && lane < 4 && c <= minPos) {  // CMOVLLE: compared (and matched) at the clamped position
+            c = minPos;
+            v = ldg_u64_unaligned(src + c);  // not the entry's position any more: read the source (8 MiB class only)
+        }
         bool f8 = false, f4 = false;
         if (lane == 0) {
             f8 = cv == v;
@@ -361,10 +395,10 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
                 const uint64_t a0 = ldg_u64_unaligned(src + i0), a1 = ldg_u64_unaligned(src + i0 + 1);
                 const uint64_t b0 = ldg_u64_unaligned(src + i1), b1 = ldg_u64_unaligned(src + i1 + 1);
                 if (lane == 0) {
-                    lTable[P.hashL(a0)] = (uint32_t)i0;
-                    sTable[P.hashS(a1)] = (uint32_t)(i0 + 1);
-                    lTable[P.hashL(b0)] = (uint32_t)i1;
-                    sTable[P.hashS(b1)] = (uint32_t)(i1 + 1);
+                    l2_put_long(lTable, P.hashL(a0), i0, a0);
+                    l2_put_short(sTable, P.hashS(a1), i0 + 1, a1);
+                    l2_put_long(lTable, P.hashL(b0), i1, b0);
+                    l2_put_short(sTable, P.hashS(b1), i1 + 1, b1);
                 }
             }
             __syncwarp();
@@ -372,7 +406,7 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
         } else if (m4 & 1u) {
             candidate = __shfl_sync(kFullMask, c, 0);
         } else if (m4 & 2u) {  // short match: try the long table at s+1 (gen.go:1665-1687)
-            if (lane == 3) lTable[h] = (uint32_t)(s + 1);
+            if (lane == 3) l2_put_long(lTable, h, s + 1, ldg_u64_unaligned(src + s + 1));
             __syncwarp();
             if (m4 & 8u) {
                 candidate = __shfl_sync(kFullMask, c, 3);
@@ -429,10 +463,10 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
             const uint64_t a0 = ldg_u64_unaligned(src + i0), a1 = ldg_u64_unaligned(src + i0 + 1);
             const uint64_t b0 = ldg_u64_unaligned(src + i1), b1 = ldg_u64_unaligned(src + i1 + 1);
             if (lane == 0) {
-                lTable[P.hashL(a0)] = (uint32_t)i0;
-                lTable[P.hashL(b0)] = (uint32_t)i1;
-                sTable[P.hashS(a1)] = (uint32_t)(i0 + 1);
-                sTable[P.hashS(b1)] = (uint32_t)(i1 + 1);
+                l2_put_long(lTable, P.hashL(a0), i0, a0);
+                l2_put_long(lTable, P.hashL(b0), i1, b0);
+                l2_put_short(sTable, P.hashS(a1), i0 + 1, a1);
+                l2_put_short(sTable, P.hashS(b1), i1 + 1, b1);
             }
             int i2 = (i0 + i1 + 1) >> 1;
             i0 += 1;
@@ -440,8 +474,8 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
             for (; i2 < i1; i0 += 2, i2 += 2) {
                 const uint64_t a = ldg_u64_unaligned(src + i0), b = ldg_u64_unaligned(src + i2);
                 if (lane == 0) {
-                    lTable[P.hashL(a)] = (uint32_t)i0;
-                    lTable[P.hashL(b)] = (uint32_t)i2;
+                    l2_put_long(lTable, P.hashL(a), i0, a);
+                    l2_put_long(lTable, P.hashL(b), i2, b);
                 }
             }
             __syncwarp();
@@ -460,8 +494,8 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
                      uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
     const int lane = lane_id();
     const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
-    uint32_t *lTable = tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4);
-    uint32_t *sTable = lTable + (1 << 17);
+    uint4 *lTable = reinterpret_cast<uint4 *>(tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4));
+    uint2 *sTable = reinterpret_cast<uint2 *>(lTable + (1 << 17));
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(counter, 1);
@@ -474,10 +508,9 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
         if (n64 > kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {  // encode_amd64.go:260
             const int n = (int)n64;
             const BetterAsmClass cls = BetterAsmClass::for_len(n);
-            uint4 *t4 = reinterpret_cast<uint4 *>(lTable);
-            for (int i = lane; i < (1 << cls.lBits) / 4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+            for (int i = lane; i < (1 << cls.lBits); i += 32) lTable[i] = make_uint4(0, 0, 0, 0);
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
-            for (int i = lane; i < (1 << cls.sBits) / 4; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+            for (int i = lane; i < (1 << cls.sBits) / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             res = encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, lane);
         }
@@ -492,8 +525,8 @@ encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
                  uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
     const int lane = lane_id();
     const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
-    uint32_t *lTable = tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4);
-    uint32_t *sTable = lTable + (1 << 17);
+    uint4 *lTable = reinterpret_cast<uint4 *>(tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4));
+    uint2 *sTable = reinterpret_cast<uint2 *>(lTable + (1 << 17));
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(counter, 1);
@@ -507,12 +540,11 @@ encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
             const int n = (int)n64;
             const bool small = n <= (64 << 10);
             // zero both tables (the small variant uses the first 2^15 / 2^12 entries)
-            uint4 *t4 = reinterpret_cast<uint4 *>(lTable);
-            const int lwords = small ? (1 << 15) : (1 << 17);
-            const int swords = small ? (1 << 12) : (1 << 14);
-            for (int i = lane; i < lwords / 4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+            const int lents = small ? (1 << 15) : (1 << 17);
+            const int sents = small ? (1 << 12) : (1 << 14);
+            for (int i = lane; i < lents; i += 32) lTable[i] = make_uint4(0, 0, 0, 0);
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
-            for (int i = lane; i < swords / 4; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+            for (int i = lane; i < sents / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             res = small ? encode_l2_block<true>(dp, sp, n, lTable, sTable, lane)
                         : encode_l2_block<false>(dp, sp, n, lTable, sTable, lane);

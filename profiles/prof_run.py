@@ -28,7 +28,7 @@ coff = torch.zeros(nblk + 1, dtype=torch.int64, device=dev)
 dec = torch.empty(nblk * bs, dtype=torch.uint8, device=dev)
 status = torch.zeros(nblk, dtype=torch.int32, device=dev)
 for _ in range(passes):
-    mz.encode_blocks_dev(src, soff, enc, eoff, out_len, mz.LevelFastest)
+    mz.encode_blocks_dev(src, soff, enc, eoff, out_len, int(os.environ.get("MINLZ_LEVEL", "1")))
     mz.pack_blocks_dev(enc, eoff, out_len, comp, coff)
     mz.decode_blocks_dev(comp, coff, dec, soff, status)
 torch.cuda.synchronize()

@@ -1,2 +1,3 @@
 O=gpurun_out; mkdir -p $O
-for v in "" _w24 _w20 _w16 _w12; do echo "== variant '$v'"; MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda$v.so timeout 300 python profiles/ab_encode.py 1 4096 1048576 json 3 2>&1 | tail -1; done | tee $O/window.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_flavor_amd64.py tests/test_stream.py -m gpu -x -q > $O/t17.log 2>&1; tail -12 $O/t17.log
+timeout 300 python profiles/ab_encode.py 2 4096 1048576 json 3 2>&1 | tail -2 | tee $O/ab17.log
