@@ -15,8 +15,7 @@
 //     (28+ warps per SM x 148 SMs >= 4096 blocks); shared-memory tables would
 //     cap the chip at ~148 chains.
 //   * the match table lives in a global-memory workspace, and every slot is a
-//     32-byte (one DRAM sector) record {position, 4 bytes before it, 24 bytes
-//     from it}.  A probe then returns the candidate AND the bytes needed to
+//     32-byte record {position, 4 bytes before it, 24 bytes from it}.  A probe then returns the candidate AND the bytes needed to
 //     verify, back-extend (<= 4) and forward-extend (<= 24) it in ONE round
 //     trip; the reference needs table -> src[candidate] -> extend.  The record
 //     is a snapshot of immutable source bytes, so results are unchanged.  This
@@ -28,6 +27,10 @@
 //     forwarded between lanes (match.any on the slot index), and only the
 //     inserts of steps that really executed are written back.
 //   * source bytes near the cursor sit in a 1 KiB per-warp shared-memory ring.
+//   * what finally bounds it (profiles/r01_micro_gather32.txt): a random 32-byte
+//     probe costs a whole 128-byte DRAM line on B200, and 32 probes per round
+//     trip x 30 k round trips x 4096 blocks move 450 GB at 92 % of the rate the
+//     DRAM sustains for random lines.
 #pragma once
 
 #include "mz_common.cuh"
@@ -574,13 +577,17 @@ __device__ __noinline__ uint32_t probe_direct(const uint8_t *src, int n, int pos
 // <= 4 back) and whether it passes the repeat check.  The warp then replays the
 // reference's control flow (search steps, back-to-back re-match probes, repeat
 // checks) over these 32 answers with warp-uniform bit tests, consuming as many
-// steps as fall inside the window; the matches it finds are queued (one per
-// lane) and turned into tokens while the NEXT batch's loads are in flight.
-// Finally the table inserts the replay performed are written back.  Inserts of
-// the same batch that alias a later probe's slot are forwarded from the ring
-// (`dup`, probe_forwarded).  The bail-out tests of the reference (dstLimit)
-// are evaluated by the token writer with the same values of d, one batch late;
-// the result (0 = incompressible) is the same.
+// steps as fall inside the window (measured: 4.1 per round trip).  A match
+// belongs to the lane of the position it was probed at; the common re-match hit
+// is a bit test plus one shuffle because every lane has prepared "a hit at my
+// position" beforehand.  At the end of the batch the owners append their
+// records to a per-warp ring in shared memory, and whenever 32 records are
+// pending they become tokens together (emit_group), in the shadow of the next
+// batch's loads.  Finally the table inserts the replay performed are written
+// back.  Inserts of the same batch that alias a later probe's slot are
+// forwarded from the ring (`dup`, probe_forwarded).  The bail-out tests of the
+// reference (dstLimit) are evaluated by the token writer with the same values
+// of d, up to 63 records late; the result (0 = incompressible) is the same.
 template <class P>
 __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, const int n, Slot *table,
                                uint32_t *ring_mem, const int lane, const int *gate, const int slice) {

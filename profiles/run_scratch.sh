@@ -1,2 +1,3 @@
 O=gpurun_out; mkdir -p $O
-MINLZ_LEVEL=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:encode_l2 -c 1 -o $O/enc_l2_full -f python profiles/prof_run.py 2048 > $O/ncu_enc_l2.log 2>&1; tail -2 $O/ncu_enc_l2.log
+echo "full:"; timeout 300 python profiles/time_decode.py | tee $O/dec_time.log
+echo "parser only (copiers idle):"; MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda_nocopy.so timeout 300 python profiles/time_decode.py | tee -a $O/dec_time.log
