@@ -1,3 +1,2 @@
 O=gpurun_out; mkdir -p $O
-echo "full:"; timeout 300 python profiles/time_decode.py | tee $O/dec_time.log
-echo "parser only (copiers idle):"; MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda_nocopy.so timeout 300 python profiles/time_decode.py | tee -a $O/dec_time.log
+timeout 600 python -m pytest tests/test_cpp_host.py -m gpu -x -q > $O/t21.log 2>&1; tail -25 $O/t21.log
