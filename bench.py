@@ -180,6 +180,55 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_funnel(args, mz, shard, dist, world, rank, dev, src, soff, enc, eoff, out_len, comp, coff, dec, status):
+    """The batch lives on rank 0: scatter raw blocks -> encode -> gather the packed stream to rank 0 ->
+    scatter it back -> decode -> gather the blocks on rank 0.  Everything inside the timed region."""
+    import torch
+    nblk, bs = args.blocks, args.block_size
+    total = world * nblk
+    parts = [torch.empty_like(src) for _ in range(world)] if rank == 0 else None
+    dist.gather(src, parts, dst=0)                      # build the full batch on rank 0 (not timed)
+    full = torch.cat(parts) if rank == 0 else None
+    del parts
+
+    def step():
+        local = shard.scatter_rows(full, total, bs, src=0, device=dev)
+        mz.encode_blocks_dev(local, soff, enc, eoff, out_len, args.level)
+        mz.pack_blocks_dev(enc, eoff, out_len, comp, coff)
+        stream, all_len, _ = shard.gather_packed(comp, out_len, total, dst=0)
+        mine, moff = shard.scatter_packed(stream, all_len, total, src=0, device=dev)
+        mz.decode_blocks_dev(mine, moff, dec, soff, status)
+        return shard.gather_rows(dec, total, bs, dst=0), stream
+
+    for _ in range(max(args.warmup, 1)):
+        back, stream = step()
+    torch.cuda.synchronize()
+    if rank == 0:
+        assert torch.equal(back, full), "funnel round trip mismatch"
+    assert int(status.abs().sum()) == 0
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        back, stream = step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0]) / args.steps
+        cfg = workload_config(args)
+        cfg["workload"] += "; FUNNEL: the batch of %d blocks lives on rank 0, raw blocks scattered and token streams / " \
+                           "decoded blocks gathered over NCCL inside every step" % total
+        print(json.dumps({"metric": METRIC, "value": round(total * bs / (ms * 1e-3) / 1e9, 4), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+                          "ratio": round(total * bs / int(stream.numel()), 4),
+                          "nccl_bytes_per_step": int(2 * (world - 1) * nblk * bs + 2 * (int(stream.numel()) * (world - 1)) // world)}))
+
+
 def workload_config(args):
     return {"workload": "configs[1]+[2]: %d x %d B synthetic %s blocks per GPU, %s encode then "
                         "batched decode of the packed token streams" %
@@ -205,6 +254,9 @@ def main():
     ap.add_argument("--flavor", default="auto", choices=("auto", "go", "amd64"),
                     help="which reference build the encoder mirrors byte for byte: the amd64 assembly (what the "
                          "reference arm runs on this box; default for levels -1/1) or the pure-Go functions")
+    ap.add_argument("--funnel", action="store_true",
+                    help="N > 1 only: the whole batch lives on rank 0 and is scattered / gathered over NCCL every step "
+                         "(SURVEY 8e 'including scatter/gather'); the default keeps the data pre-sharded")
     ap.add_argument("--cpu-blocks", type=int, default=1024, help="bounded sample for the CPU legs")
     ap.add_argument("--e2e-blocks", type=int, default=4096, help="blocks per e2e step (host buffers)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -274,6 +326,11 @@ def main():
             timed["enc"] += ev[0].elapsed_time(ev[1])
             timed["pack"] += ev[1].elapsed_time(ev[2])
             timed["dec"] += ev[2].elapsed_time(ev[3])
+
+    if args.funnel and world > 1:
+        run_funnel(args, mz, shard, dist, world, rank, dev, src, soff, enc, eoff, out_len, comp, coff, dec, status)
+        dist.destroy_process_group()
+        return
 
     for _ in range(args.warmup):
         step(None)

@@ -333,7 +333,10 @@ __device__ __forceinline__ void slot_load(const Slot *p, uint4 &a, uint4 &b) {
                  : "memory");
 }
 __device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 &b) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+#ifndef MZ_SLOT_ST
+#define MZ_SLOT_ST "st.global.v8.b32"
+#endif
+    asm volatile(MZ_SLOT_ST " [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
                  "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                  : "memory");
 }

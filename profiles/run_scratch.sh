@@ -1,2 +1,2 @@
 O=gpurun_out; mkdir -p $O
-timeout 600 python -m pytest tests/test_cpp_host.py -m gpu -x -q > $O/t21.log 2>&1; tail -25 $O/t21.log
+for v in "" _el _els; do echo "== variant '$v'"; MINLZ_CUDA_SO=$PWD/minlz_b200/libminlz_cuda$v.so timeout 300 python profiles/ab_encode.py 1 4096 1048576 json 3 2>&1 | tail -1; done | tee $O/evict.log

@@ -69,3 +69,54 @@ def test_gather_lengths_and_offsets(oracle, world):
     for rank, all_len, off in res:
         assert all_len == lens
         assert off == want_off
+
+
+def _funnel_worker(rank, world, port, nblk, bs, q):
+    """Rank 0 holds the batch: scatter raw blocks -> encode (oracle, CPU) -> gather the packed
+    stream to rank 0 -> scatter it back -> decode -> gather the blocks.  SURVEY 8(e)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import synth
+        from oracle import binding as oracle
+        full = synth.make_blocks("json", nblk, bs).reshape(-1) if rank == 0 else None
+        local = shard.scatter_rows(full, nblk, bs, src=0, device=torch.device("cpu"))
+        lo, hi = shard.block_range(nblk, rank, world)
+        assert local.numel() == (hi - lo) * bs
+        toks = [oracle.encode_block(local[i * bs:(i + 1) * bs].numpy(), 1) for i in range(hi - lo)]
+        packed = torch.from_numpy(np.frombuffer(b"".join(toks) + b"\0", dtype=np.uint8).copy())
+        lens = torch.tensor([len(t) for t in toks], dtype=torch.int32)
+        stream, all_len, off = shard.gather_packed(packed, lens, nblk, dst=0)
+        if rank == 0:
+            want = b"".join(oracle.encode_block(full[i * bs:(i + 1) * bs].numpy(), 1) for i in range(nblk))
+            assert stream.numpy().tobytes() == want and int(off[-1]) == len(want)
+        else:
+            assert stream is None
+        mine, moff = shard.scatter_packed(stream, all_len, nblk, src=0, device=torch.device("cpu"))
+        assert mine.numpy().tobytes() == b"".join(toks) and moff.tolist()[-1] == mine.numel()
+        dec = bytearray()
+        for i in range(hi - lo):
+            st, out = oracle.decode_block(mine[int(moff[i]):int(moff[i + 1])].numpy(), bs)
+            assert st == 0
+            dec += out
+        back = shard.gather_rows(torch.from_numpy(np.frombuffer(bytes(dec) + b"\0", dtype=np.uint8).copy()), nblk, bs, dst=0)
+        ok = True if rank != 0 else bool(torch.equal(back, full))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nblk", [(2, 7), (3, 2), (3, 8)])
+def test_funnel_scatter_gather(world, nblk):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_funnel_worker, args=(r, world, port, nblk, 1 << 14, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
