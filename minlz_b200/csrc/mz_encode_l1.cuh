@@ -459,9 +459,6 @@ __device__ __noinline__ uint32_t probe_forwarded(const uint32_t *ring_mem, int p
 // token-at-a-time writer, and the work moves out of the walk's dependency chain.
 constexpr int kRecRing = 64;  // records per warp (>= 31 pending + 9 new per batch)
 
-#ifndef MZ_ENC_GROUP_EMIT
-#define MZ_ENC_GROUP_EMIT 1
-#endif
 
 // Emits `cnt` (1..32) records held one per lane.  Returns false when a bail-out test fires.
 template <class P>
@@ -627,15 +624,9 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
     // (positions only grow within a batch, so lane order = stream order): the owner lane
     // holds [o_base, o_end) and o_rep = offset | kind << 24; `mmask` marks the owners.
     // (the literals of a match start where the previous one ended: emitted)
-#if !MZ_ENC_GROUP_EMIT
-    int q_base = 0, q_rep = 0, q_end = 0;
-    int q_cnt = 0;
-#endif
     int emitted = 0;  // nextEmit as the token writer sees it
-#if MZ_ENC_GROUP_EMIT
     uint32_t *recs = ring_mem + kRingWords + kRingMirror;  // [3][kRecRing]: base, offset | kind << 24, end
     int r_head = 0, r_pending = 0;
-#endif
 
     const unsigned below = (1u << lane) - 1u;
     const unsigned above = ~((2u << lane) - 1u);
@@ -680,7 +671,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         }
 
         // ---------------- the loads are in flight: write queued tokens ----------------
-#if MZ_ENC_GROUP_EMIT
         while (r_pending >= 32 || (done && r_pending > 0)) {
             const int cnt = min(r_pending, 32);
             const int r = (r_head + lane) & (kRecRing - 1);
@@ -690,40 +680,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             r_pending -= cnt;
         }
         __syncwarp();
-#else
-        for (int i = 0; i < q_cnt; i++) {
-            const int base = __shfl_sync(kFullMask, q_base, i);
-            const int rk = __shfl_sync(kFullMask, q_rep, i);
-            const int end = __shfl_sync(kFullMask, q_end, i);
-            const int kind = rk >> 24, rep = rk & 0xffffff;  // kind 3: literals + repeat, 0: (literals +) copy
-            const int ne = emitted;
-            emitted = end;
-            const int length = end - base;
-            if (kind) {  // :94-145; Asm: gen.go:614-624 checkDst(litLen)
-                if (P::kAsm ? d + (base - ne) + prm.lit_overhead() >= dstLimit : d + (base - ne) > dstLimit) return 0;
-                d += emit_literal(dst + d, src + ne, base - ne, lane, prm.lit_quirk());
-                d += emit_repeat(dst + d, length, lane);
-                continue;
-            }
-            if (P::kAsm && d >= dstLimit) return 0;  // gen.go:828 (and :1039 with the same d)
-            if (ne != base) {  // :190-206
-                if (base - ne > prm.max_fuse_lits() || rep < kMinCopy2Offset) {
-                    if (P::kAsm ? d + (base - ne) + prm.lit_overhead() >= dstLimit : d + (end - ne) > dstLimit) return 0;
-                    d += emit_literal(dst + d, src + ne, base - ne, lane, prm.lit_quirk());
-                    d += emit_copy(dst + d, rep, length, lane);
-                } else if (rep <= kMaxCopy2Offset) {
-                    d += emit_copy_lits2(dst + d, src + ne, base - ne, rep, length, lane);
-                } else {
-                    d += emit_copy_lits3(dst + d, src + ne, base - ne, rep, length, lane);
-                }
-            } else {
-                d += emit_copy(dst + d, rep, length, lane);
-            }
-            // :229, first thing the re-match loop does; Asm: gen.go:955-975
-            if (end < sLimit && (P::kAsm ? d >= dstLimit : d > dstLimit)) return 0;
-        }
-        q_cnt = 0;
-#endif
         if (done) break;
 
         const unsigned same = __match_any_sync(kFullMask, h);
@@ -776,7 +732,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         int rep_snap = 0;     // repeat checks come from the last match's snapshot (Rnz, Rps)
         uint32_t Rnz = 0;
         int Rps = 0;
-#if MZ_ENC_GROUP_EMIT
         // Every lane prepares the record of "a re-match hit at my position" up front: the match
         // starts at p (no literals, no backward extension in the re-match loop), runs for the
         // f_own equal snapshot bytes and has offset p - cand.  The replay then only needs the
@@ -798,7 +753,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                 Rlane = -1;
             }
         };
-#endif
 
         // Probe of lane L against the table as of `ins_at`: hit flag; when the slot was
         // written earlier in this batch the candidate is that insert (*fcand, *fnz).
@@ -851,7 +805,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                         break;
                     }
                     ENC_STAT(1);
-#if MZ_ENC_GROUP_EMIT
                     if (!((cold >> L) & 1u)) {  // fast: everything this step needs is already in lane L
                         ins |= 5u << (L - 2);
                         if (!((ER >> L) & 1u)) {
@@ -865,7 +818,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                         continue;
                     }
                     settle();
-#endif
                     int fcand = -1;
                     uint32_t fnz = 0;
                     bool hit = (ER >> L) & 1u;  // read before this step's inserts (:236-239)
@@ -886,17 +838,8 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                     const int f = mnz ? __ffs(mnz) - 1 : kSnapFwd;
                     repeat = s - mcand;
                     const int e = match_end(s, f, f, repeat);
-#if MZ_ENC_GROUP_EMIT
                     if (lane == L) o_base = s, o_rep = repeat, o_end = e;
                     mmask |= 1u << L;
-#else
-                    if (lane == q_cnt) {
-                        q_base = s;
-                        q_rep = repeat;
-                        q_end = e;
-                    }
-                    q_cnt++;
-#endif
                     rep_snap = 1;
                     Rnz = mnz;
                     Rps = s;
@@ -906,9 +849,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             }
 
             // ---- one search step at t (:70-160) ----
-#if MZ_ENC_GROUP_EMIT
             settle();
-#endif
             const int t = s;
             const int L = t - wbase;
             const int nextS = t + ((t - nextEmit) >> prm.skip_log()) + prm.step();  // :79
@@ -940,17 +881,8 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                 if (!P::kAsm || P::kBackExtend) base -= extend_backward(src, base - repeat, base, nextEmit, lane);
                 s = P::kAsm ? extend_forward_exact(src, t + 5, t + 5 - repeat, n, lane, gate, slice)  // gen.go:632-660
                             : extend_forward8(src, t + 5, t + 5 - repeat, sLimit, lane, gate, slice);
-#if MZ_ENC_GROUP_EMIT
                 if (lane == L + 1) o_base = base, o_rep = repeat | 3 << 24, o_end = s;  // probed at t+1
                 mmask |= 2u << L;
-#else
-                if (lane == q_cnt) {
-                    q_base = base;
-                    q_rep = repeat | 3 << 24;
-                    q_end = s;
-                }
-                q_cnt++;
-#endif
                 nextEmit = s;
                 if (s >= sLimit) {
                     done = true;
@@ -1024,17 +956,8 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             }
             repeat = mps - mcand;
             const int e = match_end(base, known, f, repeat);
-#if MZ_ENC_GROUP_EMIT
             if (lane == mps - wbase) o_base = base, o_rep = repeat, o_end = e;
             mmask |= 1u << (mps - wbase);
-#else
-            if (lane == q_cnt) {
-                q_base = base;
-                q_rep = repeat;
-                q_end = e;
-            }
-            q_cnt++;
-#endif
             rep_snap = 1;
             Rnz = mnz;
             Rps = mps;
@@ -1042,7 +965,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             rematch = true;
         }
 
-#if MZ_ENC_GROUP_EMIT
         settle();  // `repeat` feeds the next batch's repeat-check loads
         if (mmask) {  // append this batch's matches to the record ring, in lane (= stream) order
             if ((mmask >> lane) & 1u) {
@@ -1053,7 +975,6 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             }
             r_pending += __popc(mmask);
         }
-#endif
         // ---------------- write back the inserts the replay performed ----------------
         if (((ins >> lane) & 1u) && (same & ins & above) == 0) {  // a later insert on the same slot wins
             slot_store(table + h, make_uint4((uint32_t)p, W[0], W[1], W[2]), make_uint4(W[3], W[4], W[5], W[6]));
