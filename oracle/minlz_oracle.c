@@ -1006,6 +1006,7 @@ static int64_t encode_l2(uint8_t *dst, const uint8_t *src, int n, int lBits, int
         int candidateL = 0;
         int nextS = 0;
         for (;;) {
+            STAT(0); /* L2 search steps (shares the counter array with L1) */
             nextS = s + ((s - nextEmit) >> 7) + 1; /* :114 */
             if (nextS > sLimit) goto emit_remainder;
             int minSrcPos = s - kMaxCopy3Offset + 1; /* :118 */
@@ -1087,6 +1088,10 @@ static int64_t encode_l2(uint8_t *dst, const uint8_t *src, int n, int lBits, int
         s += 4;
         candidateL += 4;
         s = extend_tail(src, n, s, candidateL); /* :239-254 */
+#ifdef MZO_STATS
+        STAT(2);
+        mzo_stats[12] += (uint64_t)(s - base);
+#endif
 
         /* :257-264 drop far 4-byte matches */
         if (offset > 65535 && s - base <= 4 && repeat != offset) {
