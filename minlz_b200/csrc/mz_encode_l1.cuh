@@ -195,12 +195,15 @@ template <bool kSmall>
 struct L1Params {
     static constexpr bool kAsm = false;
     static constexpr bool kMayClamp = false;
+    static constexpr bool kBalanced = false;
     static constexpr int kMinMatch = 4;         // candidates are verified on 4 bytes
     static constexpr bool kBackExtend = true;   // :169-172
     __device__ __forceinline__ int table_bits() const { return kSmall ? 13 : 15; }
     __device__ __forceinline__ int skip_log() const { return kSmall ? 5 : 6; }
     __device__ __forceinline__ int step() const { return 4; }
     __device__ __forceinline__ int max_fuse_lits() const { return kSmall ? kMaxCopy2Lits : kMaxCopy3Lits; }
+    __device__ __forceinline__ int max_fuse_lits2() const { return max_fuse_lits(); }
+    __device__ __forceinline__ int max_fuse_lits3() const { return max_fuse_lits(); }
     __device__ __forceinline__ int s_limit(int n) const { return n - kInputMargin; }
     __device__ __forceinline__ int dst_limit(int n) const { return n - (n >> 5) - 6; }
     __device__ __forceinline__ int lit_overhead() const { return 0; }
@@ -214,12 +217,15 @@ template <bool kClamp>  // kClamp: the 8 MiB class (encodeBlockAsm), whose far c
 struct L1AsmBigParams {
     static constexpr bool kAsm = true;
     static constexpr bool kMayClamp = kClamp;
+    static constexpr bool kBalanced = false;
     static constexpr int kMinMatch = 4;
     static constexpr bool kBackExtend = true;
     __device__ __forceinline__ int table_bits() const { return 15; }
     __device__ __forceinline__ int skip_log() const { return 6; }
     __device__ __forceinline__ int step() const { return 4; }
     __device__ __forceinline__ int max_fuse_lits() const { return 3; }            // gen.go:907
+    __device__ __forceinline__ int max_fuse_lits2() const { return 3; }
+    __device__ __forceinline__ int max_fuse_lits3() const { return 3; }
     __device__ __forceinline__ int s_limit(int n) const { return n - 17; }        // gen.go:369
     __device__ __forceinline__ int dst_limit(int n) const { return n - 17 - (n >> 5); }  // gen.go:380-391
     __device__ __forceinline__ int lit_overhead() const { return 4; }             // gen.go:1157-1169
@@ -234,6 +240,7 @@ template <bool kMatch8>
 struct AsmClassParams {
     static constexpr bool kAsm = true;
     static constexpr bool kMayClamp = kMatch8;  // only the Fast dispatch sends blocks > 2 MiB here
+    static constexpr bool kBalanced = false;
     static constexpr int kMinMatch = kMatch8 ? 8 : 4;
     static constexpr bool kBackExtend = !kMatch8;
     int tb, sl, st, hb, ovh;
@@ -242,6 +249,8 @@ struct AsmClassParams {
     __device__ __forceinline__ int skip_log() const { return sl; }
     __device__ __forceinline__ int step() const { return st; }
     __device__ __forceinline__ int max_fuse_lits() const { return kMatch8 ? 0 : 3; }
+    __device__ __forceinline__ int max_fuse_lits2() const { return max_fuse_lits(); }
+    __device__ __forceinline__ int max_fuse_lits3() const { return max_fuse_lits(); }
     __device__ __forceinline__ int s_limit(int n) const { return n - 17; }
     __device__ __forceinline__ int dst_limit(int n) const { return n - 17 - (n >> (kMatch8 ? 3 : 5)); }
     __device__ __forceinline__ int lit_overhead() const { return ovh; }
@@ -282,12 +291,15 @@ template <bool kSmall>
 struct L0Params {
     static constexpr bool kAsm = false;
     static constexpr bool kMayClamp = false;
+    static constexpr bool kBalanced = false;
     static constexpr int kMinMatch = 8;
     static constexpr bool kBackExtend = false;  // encode_l0.go:164 `for false && ...`
     __device__ __forceinline__ int table_bits() const { return kSmall ? 12 : 13; }
     __device__ __forceinline__ int skip_log() const { return kSmall ? 4 : 5; }
     __device__ __forceinline__ int step() const { return kSmall ? 4 : 5; }
     __device__ __forceinline__ int max_fuse_lits() const { return kSmall ? kMaxCopy2Lits : kMaxCopy3Lits; }
+    __device__ __forceinline__ int max_fuse_lits2() const { return max_fuse_lits(); }
+    __device__ __forceinline__ int max_fuse_lits3() const { return max_fuse_lits(); }
     __device__ __forceinline__ int s_limit(int n) const { return n - kInputMargin; }
     __device__ __forceinline__ int dst_limit(int n) const { return kSmall ? n - (n >> 4) - 32 : n - (n >> 3) - 6; }
     __device__ __forceinline__ int lit_overhead() const { return 0; }
@@ -471,11 +483,13 @@ __device__ __forceinline__ bool emit_group(const P prm, uint8_t *dst, const uint
     const int kind = rk >> 24, rep = rk & 0xffffff;  // kind 3: literals + repeat, 0: (literals +) copy
     const int litLen = valid ? base - ne : 0;
     const int length = end - base;
-    bool sep = false, fused2 = false, fused3 = false;  // how the literals travel (:190-206)
+    // how the literals travel: L1 / L0 encode_l1.go:190-206 (one limit for both fused forms),
+    // L2 encode_l2.go:266-289 / gen.go:1803-1866 (<= 4 with a copy2, <= 3 with a copy3)
+    bool sep = false, fused2 = false, fused3 = false;
     if (valid && litLen > 0) {
-        if (kind || litLen > prm.max_fuse_lits() || rep < kMinCopy2Offset) sep = true;
-        else if (rep <= kMaxCopy2Offset) fused2 = true;
-        else fused3 = true;
+        if (kind || rep < kMinCopy2Offset) sep = true;
+        else if (rep <= kMaxCopy2Offset) (litLen <= prm.max_fuse_lits2() ? fused2 : sep) = true;
+        else (litLen <= prm.max_fuse_lits3() ? fused3 : sep) = true;
     }
     uint64_t lh = 0, tok = 0, post = 0;
     int n_lh = 0, n_tok = 0, n_post = 0;
@@ -510,12 +524,16 @@ __device__ __forceinline__ bool emit_group(const P prm, uint8_t *dst, const uint
     bool fail = false;
     if (valid) {
         const int ovh = prm.lit_overhead();
-        if (kind) {  // :103; Asm: gen.go:614-624 checkDst(litLen)
+        if (kind) {  // :103 / encode_l2.go:147; Asm: gen.go:614-624,1490-1508 checkDst(litLen)
             fail = P::kAsm ? d0 + litLen + ovh >= dstLimit : d0 + litLen > dstLimit;
         } else {
-            if (P::kAsm && d0 >= dstLimit) fail = true;  // gen.go:828 (and :1039 with the same d)
-            if (sep && (P::kAsm ? d0 + litLen + ovh >= dstLimit : d0 + (end - ne) > dstLimit)) fail = true;  // :194
-            // :229, first thing the re-match loop does; Asm: gen.go:955-975
+            if (P::kBalanced) {  // before every match: encode_l2.go:229; Asm: gen.go:1720-1737
+                if (P::kAsm ? d0 + litLen + ovh >= dstLimit : d0 + litLen > dstLimit) fail = true;
+            } else {
+                if (P::kAsm && d0 >= dstLimit) fail = true;  // gen.go:828 (and :1039 with the same d)
+                if (sep && (P::kAsm ? d0 + litLen + ovh >= dstLimit : d0 + (end - ne) > dstLimit)) fail = true;  // :194
+            }
+            // after the copy (:229 / encode_l2.go:293-297; Asm: gen.go:955-975,1899-1918)
             if (end < sLimit && (P::kAsm ? d0 + total >= dstLimit : d0 + total > dstLimit)) fail = true;
         }
     }

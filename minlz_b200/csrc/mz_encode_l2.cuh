@@ -87,10 +87,65 @@ __device__ __forceinline__ int extend_to_end(const uint8_t *src, int n, int s, i
     }
 }
 
+// ---- token records ------------------------------------------------------------
+// As in the L1 kernel the walk only RECORDS its matches (base, end, offset | kind << 24) in a
+// per-warp ring in shared memory; 32 at a time they become tokens in emit_group (lane = record,
+// prefix-sum positions, the reference's bail-out tests per lane with the serial values of d).
+// A match the walk drops (far 4-byte match) leaves no record: its dst test would have failed
+// only if the next record's or the remainder's test fails too (d unchanged, literals only grow).
+struct L2EmitGo {
+    static constexpr bool kAsm = false, kBalanced = true;
+    __device__ __forceinline__ int max_fuse_lits2() const { return kMaxCopy2Lits; }  // encode_l2.go:268
+    __device__ __forceinline__ int max_fuse_lits3() const { return kMaxCopy3Lits; }  // :279
+    __device__ __forceinline__ int lit_overhead() const { return 0; }
+    __device__ __forceinline__ bool lit_quirk() const { return false; }
+};
+struct L2EmitAsm {
+    static constexpr bool kAsm = true, kBalanced = true;
+    int ovh;
+    bool quirk;
+    __device__ __forceinline__ int max_fuse_lits2() const { return 4; }  // gen.go:1822
+    __device__ __forceinline__ int max_fuse_lits3() const { return 3; }  // gen.go:1850
+    __device__ __forceinline__ int lit_overhead() const { return ovh; }
+    __device__ __forceinline__ bool lit_quirk() const { return quirk; }
+};
+struct L2Records {
+    uint32_t *recs;  // [3][kRecRing] in shared memory
+    int head, pending;
+    __device__ __forceinline__ void push(int base, int rk, int end, int lane) {
+        if (lane == 0) {
+            const int w = (head + pending) & (kRecRing - 1);
+            recs[w] = (uint32_t)base;
+            recs[kRecRing + w] = (uint32_t)rk;
+            recs[2 * kRecRing + w] = (uint32_t)end;
+        }
+        pending++;
+        __syncwarp();
+    }
+    // Emits full groups of 32 (everything when `all`).  Returns false when a bail-out test fires.
+    template <class E>
+    __device__ __forceinline__ bool flush(const E prm, uint8_t *dst, const uint8_t *src, int &d, int &emitted, int lane,
+                                          int sLimit, int dstLimit, bool all) {
+        while (pending >= 32 || (all && pending > 0)) {
+            const int cnt = min(pending, 32);
+            const int r = (head + lane) & (kRecRing - 1);
+            const int g_base = (int)recs[r], g_rk = (int)recs[kRecRing + r], g_end = (int)recs[2 * kRecRing + r];
+            if (!emit_group(prm, dst, src, d, emitted, g_base, g_rk, g_end, cnt, lane, sLimit, dstLimit)) return false;
+            head = (head + cnt) & (kRecRing - 1);
+            pending -= cnt;
+            __syncwarp();
+        }
+        return true;
+    }
+};
+
 template <bool kSmall>
 __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, uint4 *lTable, uint2 *sTable,
-                               const int lane) {
+                               uint32_t *rec_mem, const int lane) {
     using P = L2Params<kSmall>;
+    L2Records q{rec_mem, 0, 0};
+    const L2EmitGo ep{};
+    int emitted = 0;  // nextEmit as the token writer sees it
     const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
     const int sLimit = n - kInputMargin;
     const int dstLimit = n - (n >> 5) - 6;
@@ -154,11 +209,10 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
             if (m4 & 4u) {  // repeat at s+1 (:139-196)
                 int base = s + 1;
                 base -= extend_backward(src, base - repeat, base, nextEmit, lane);
-                if (d + (base - nextEmit) > dstLimit) return 0;
-                d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane);
                 const int cand = s - repeat + 4 + 1;
                 s = extend_to_end(src, n, s + 4 + 1, cand, lane);
-                d += emit_repeat(dst + d, s - base, lane);
+                q.push(base, repeat | 3 << 24, s, lane);  // :147 test, literals and the repeat token: emit_group
+                if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
                 nextEmit = s;
                 if (s >= sLimit) goto emit_remainder;
                 // index in-between (:183-195); program order of one lane keeps "later write wins"
@@ -204,8 +258,7 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
             candidateL -= back;
             s -= back;
         }
-        if (d + (s - nextEmit) > dstLimit) return 0;  // :229
-        {
+        {   // the :229 test travels with the record
             const int base = s;
             const int offset = base - candidateL;
             s = extend_to_end(src, n, s + 4, candidateL + 4, lane);  // :239-254
@@ -217,30 +270,11 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
                 continue_outer = true;
             }
             if (!continue_outer) {
-                const int nlits = base - nextEmit;  // :266-289
-                if (nlits > 0) {
-                    if (offset <= kMaxCopy2Offset) {
-                        if (nlits > kMaxCopy2Lits || offset < 64) {
-                            d += emit_literal(dst + d, src + nextEmit, nlits, lane);
-                            d += emit_copy(dst + d, offset, s - base, lane);
-                        } else {
-                            d += emit_copy_lits2(dst + d, src + nextEmit, nlits, offset, s - base, lane);
-                        }
-                    } else {
-                        if (nlits > kMaxCopy3Lits) {
-                            d += emit_literal(dst + d, src + nextEmit, nlits, lane);
-                            d += emit_copy(dst + d, offset, s - base, lane);
-                        } else {
-                            d += emit_copy_lits3(dst + d, src + nextEmit, nlits, offset, s - base, lane);
-                        }
-                    }
-                } else {
-                    d += emit_copy(dst + d, offset, s - base, lane);
-                }
+                q.push(base, offset, s, lane);  // :266-289 and the :297 test: emit_group
+                if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
                 repeat = offset;
                 nextEmit = s;
                 if (s >= sLimit) goto emit_remainder;  // :293
-                if (d > dstLimit) return 0;            // :297
 
                 // index short & long (:303-326)
                 int index0 = base + 1;
@@ -274,6 +308,7 @@ __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, ui
     }
 
 emit_remainder:  // :329-337
+    if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, true)) return 0;
     if (nextEmit < n) {
         if (d + n - nextEmit > dstLimit) return 0;
         d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane);
@@ -321,8 +356,11 @@ struct BetterAsmClass {
 };
 
 __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const uint8_t *src, const int n,
-                                   uint4 *lTable, uint2 *sTable, const int lane) {
+                                   uint4 *lTable, uint2 *sTable, uint32_t *rec_mem, const int lane) {
     const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
+    L2Records q{rec_mem, 0, 0};
+    const L2EmitAsm ep{P.ovh, P.quirk};
+    int emitted = 0;  // nextEmit as the token writer sees it
     const int sLimit = n - P.inMargin;                    // gen.go:1272-1282
     const int dstLimit = n - P.outMargin - (n >> 5);      // gen.go:1284-1297
     int nextEmit = 0;
@@ -385,10 +423,9 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
         } else if (m4 & 4u) {  // repeat at s+1 (gen.go:1445-1622)
             int base = s + 1;
             base -= extend_backward(src, base - repeat, base, nextEmit, lane);
-            if (d + (base - nextEmit) + P.ovh >= dstLimit) return 0;
-            d += emit_literal(dst + d, src + nextEmit, base - nextEmit, lane, P.quirk);
             s = extend_to_end(src, n, s + 5, s + 5 - repeat, lane);
-            d += emit_repeat(dst + d, s - base, lane);
+            q.push(base, repeat | 3 << 24, s, lane);  // gen.go:1490-1508 test, literals, repeat token: emit_group
+            if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
             nextEmit = s;
             if (s >= sLimit) break;
             for (int i0 = base + 1, i1 = s - 2; i0 < i1; i0 += 2, i1 -= 2) {
@@ -425,8 +462,7 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
             candidate -= back;
             s -= back;
         }
-        if (d + (s - nextEmit) + P.ovh >= dstLimit) return 0;
-        const int base = s;
+        const int base = s;  // the gen.go:1720-1737 test travels with the record
         const int offset = base - candidate;
         s = extend_to_end(src, n, s + 4, candidate + 4, lane);
         if (P.far3 && s - base == 4 && offset > kMaxCopy2Offset && offset != repeat) {  // gen.go:1786-1801
@@ -434,30 +470,10 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
             continue;
         }
         repeat = offset;
-        {
-            const int nlits = base - nextEmit, length = s - base;
-            if (nlits == 0) {
-                d += emit_copy(dst + d, offset, length, lane);
-            } else if (offset < kMinCopy2Offset) {
-                d += emit_literal(dst + d, src + nextEmit, nlits, lane, P.quirk);
-                d += emit_copy(dst + d, offset, length, lane);
-            } else if (P.far3 && offset > kMaxCopy2Offset) {
-                if (nlits > 3) {
-                    d += emit_literal(dst + d, src + nextEmit, nlits, lane, P.quirk);
-                    d += emit_copy(dst + d, offset, length, lane);
-                } else {
-                    d += emit_copy_lits3(dst + d, src + nextEmit, nlits, offset, length, lane);
-                }
-            } else if (nlits > 4) {
-                d += emit_literal(dst + d, src + nextEmit, nlits, lane, P.quirk);
-                d += emit_copy(dst + d, offset, length, lane);
-            } else {
-                d += emit_copy_lits2(dst + d, src + nextEmit, nlits, offset, length, lane);
-            }
-        }
+        q.push(base, offset, s, lane);  // gen.go:1803-1897 and the :1905-1918 test: emit_group
+        if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
         nextEmit = s;
         if (s >= sLimit) break;
-        if (d >= dstLimit) return 0;
         {   // index the match interior (gen.go:1921-1978); one lane keeps "later write wins"
             int i0 = base + 1, i1 = s - 2;
             const uint64_t a0 = ldg_u64_unaligned(src + i0), a1 = ldg_u64_unaligned(src + i0 + 1);
@@ -483,6 +499,7 @@ __device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const u
     }
 
     // emit_remainder (gen.go:1980-2017): the bail test runs even when nothing is left
+    if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, true)) return 0;
     if (d + (n - nextEmit) + P.ovh >= dstLimit) return 0;
     d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane, P.quirk);
     return d;
@@ -492,6 +509,7 @@ __global__ void __launch_bounds__(kEncL2Warps * 32)
 encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                      const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                      uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
+    __shared__ uint32_t rec_rings[kEncL2Warps][3 * kRecRing];
     const int lane = lane_id();
     const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
     uint4 *lTable = reinterpret_cast<uint4 *>(tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4));
@@ -512,7 +530,7 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
             for (int i = lane; i < (1 << cls.sBits) / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
-            res = encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, lane);
+            res = encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
@@ -523,6 +541,7 @@ __global__ void __launch_bounds__(kEncL2Warps * 32)
 encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                  uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
+    __shared__ uint32_t rec_rings[kEncL2Warps][3 * kRecRing];
     const int lane = lane_id();
     const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
     uint4 *lTable = reinterpret_cast<uint4 *>(tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4));
@@ -546,8 +565,8 @@ encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
             for (int i = lane; i < sents / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
-            res = small ? encode_l2_block<true>(dp, sp, n, lTable, sTable, lane)
-                        : encode_l2_block<false>(dp, sp, n, lTable, sTable, lane);
+            res = small ? encode_l2_block<true>(dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
+                        : encode_l2_block<false>(dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
