@@ -163,3 +163,24 @@ def test_repeat_lengths(oracle):
         pre = b"\x00z"  # literal 'z', then repeat with offset 1
         st, out = oracle.decode_block(pre + dst[:n].tobytes(), 1 + length)
         assert st == 0 and out == b"z" * (1 + length)
+
+
+def test_asm_flavour_matches_recorded_reference_output(oracle):
+    """tests/golden/asm_digests.json holds digests of what the reference's real amd64 assembly
+    emitted (recorded through oracle/_ref by tests/golden/make_asm_golden.py).  The restated
+    amd64 flavour must reproduce every one of them -- this pins it to reference output even
+    where oracle/_ref cannot be built."""
+    import hashlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_asm_golden
+    rec = json.load(open(corpus.golden_path("asm_digests.json")))["digests"]
+    items = make_asm_golden.inputs()
+    assert len(items) == len(rec) > 150
+    for name, data in items:
+        assert rec[name]["n"] == len(data)
+        for level in (-1, 1, 2):
+            got = hashlib.sha256(oracle.encode_block(data, level, flavor="asm")).hexdigest()
+            assert got == rec[name][str(level)], (name, level)

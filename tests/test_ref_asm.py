@@ -246,3 +246,17 @@ def test_go_flavour_against_real_decoder_and_prefix(oracle):
             a, g = refasm.encode_block(blk, 1), oracle.encode_block(blk, 1)
             same = next((i for i in range(min(len(a), len(g))) if a[i] != g[i]), min(len(a), len(g)))
             assert same >= len(a) - 64, "Go and asm L1 flavours should only differ in the block tail"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/testdata/fuzz"), reason="reference checkout not present")
+def test_encoders_identical_full_fuzz_corpora(oracle):
+    """The reference's complete block corpora (fuzz_test.go:31 FuzzEncodingBlocks seeds), not the
+    committed samples: every input, all three levels, byte-identical to the real assembly."""
+    n = 0
+    for name in ("block-corpus-raw.zip", "block-corpus-enc.zip"):
+        for tag, data in corpus.load_zip("/root/reference/testdata/fuzz/" + name):
+            if len(data) < 17 or len(data) > (1 << 20):
+                continue
+            _same_encoders(oracle, np.frombuffer(data, dtype=np.uint8), tag)
+            n += 1
+    assert n > 900
