@@ -673,7 +673,12 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             ring.ensure(min(wbase + 320, fill_limit), lane);
             ring.fetch28(p - 4, W);
             h = prm.hash((uint64_t)W[2] << 32 | W[1]);
-            if (active) slot_load(table + h, ea, eb);
+            // Positions this batch can never PROBE do not fetch their slot (a probe = a DRAM line):
+            // in re-match mode the window starts at s-2, and s-2 / s-1 are only ever inserted
+            // (:236-239); in search mode the step probes t, t+1, t+2 and whatever follows -- the next
+            // step at nextS >= t + step, or the end of a match of >= 4 bytes -- lies at t + step or beyond.
+            const bool never = rematch ? lane < 2 : (lane >= 3 && lane < prm.step());
+            if (active && !never) slot_load(table + h, ea, eb);
             if (rep_lane) {
                 // (the funnel shift would wait for the load right here: keep the raw words)
                 const uintptr_t ra = reinterpret_cast<uintptr_t>(src + p - repeat);
