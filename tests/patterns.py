@@ -117,3 +117,45 @@ def roundtrip_inputs():
     far[2450000:2460000] = far[100000:110000]
     out.append(("far_matches", bytes(far)))
     return out
+
+
+def random_structure(rng, max_n=2500000):
+    """One input of a fuzz campaign (fuzz_test.go:31 FuzzEncodingBlocks in spirit): a random size
+    over every encoder size class and one of six structures -- noise, a small alphabet, phrases from
+    a vocabulary, noise with pasted copies at offsets / lengths around every token boundary
+    (1, 63/64/65, 1024/1025, 65535..65600, far), byte runs, a noisy period."""
+    kind = int(rng.integers(0, 6))
+    n = int(rng.choice([rng.integers(17, 200), rng.integers(200, 5000), rng.integers(5000, 70000),
+                        rng.integers(70000, 600000), rng.integers(600000, max_n)], p=[0.2, 0.3, 0.3, 0.15, 0.05]))
+    if kind == 0:
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+    elif kind == 1:
+        d = (rng.integers(0, int(rng.integers(2, 20)), n, dtype=np.uint8) + 48).astype(np.uint8)
+    elif kind == 2:
+        vocab = [rng.integers(97, 123, int(rng.integers(2, 12)), dtype=np.uint8) for _ in range(int(rng.integers(4, 400)))]
+        parts, tot = [], 0
+        while tot < n:
+            w = vocab[int(rng.integers(0, len(vocab)))]
+            parts += [w, np.array([32], dtype=np.uint8)]
+            tot += len(w) + 1
+        d = np.concatenate(parts)[:n]
+    elif kind == 3:
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        for _ in range(int(n * rng.uniform(0.001, 0.05))):
+            ln = int(rng.choice([4, 5, 6, 7, 8, 9, 11, 12, 13, 20, 24, 25, 40, 64, 65, 300, 5000]))
+            if n < ln + 2:
+                continue
+            p = int(rng.integers(1, n - ln))
+            off = min(int(rng.choice([1, 2, 3, 4, 8, 63, 64, 65, 1000, 1024, 1025, 65535, 65536, 65599, 65600, 70000, max(1, p)])), p)
+            for k in range(ln):
+                d[p + k] = d[p + k - off]
+    elif kind == 4:
+        d = np.repeat(rng.integers(0, 256, n // 3 + 1, dtype=np.uint8), rng.integers(1, 9, n // 3 + 1))[:n]
+        if d.size < 17:
+            d = np.zeros(17, dtype=np.uint8)
+    else:
+        per = rng.integers(0, 256, int(rng.integers(1, 3000)), dtype=np.uint8)
+        d = np.tile(per, n // per.size + 1)[:n].copy()
+        idx = rng.integers(0, n, int(n * rng.uniform(0, 0.02)))
+        d[idx] = rng.integers(0, 256, idx.size, dtype=np.uint8)
+    return np.ascontiguousarray(d, dtype=np.uint8)

@@ -103,6 +103,13 @@ def test_flavour_8mib_class(oracle):
     _check(oracle, items)
 
 
+def test_flavour_random_structures(oracle):
+    """A fuzz batch: 300 random structures over every size class, all three levels, in batched calls."""
+    rng = np.random.default_rng(2026)
+    items = [(("fuzz", i), patterns.random_structure(rng, max_n=1200000).tobytes()) for i in range(300)]
+    _check(oracle, items)
+
+
 def test_flavour_bailouts(oracle):
     """Barely compressible inputs around dstLimit: every bail test of gen.go:395-417 decides somewhere."""
     rng = np.random.default_rng(11)

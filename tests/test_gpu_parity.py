@@ -403,3 +403,16 @@ def test_random_structures_roundtrip(oracle):
         out, status = mz.decode_blocks(csrc, csoff, cdoff)
         assert not status.any()
         assert out.tobytes() == b"".join(raws)
+
+
+def test_random_structures_fuzz_batch(oracle):
+    """The fuzz generator of tests/patterns.py (every size class, six structures): 300 inputs, all
+    three levels, encoder bytes == oracle (Go flavour) in batched calls."""
+    rng = np.random.default_rng(4242)
+    blocks = [patterns.random_structure(rng, max_n=1200000).tobytes() for _ in range(300)]
+    src, soff = _cat(blocks)
+    for level in (-1, 1, 2):
+        dst, doff, out_len = mz.encode_blocks(src, soff, level)
+        for i, data in enumerate(blocks):
+            got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
+            assert got == oracle.encode_block(data, level), (level, i, len(data))

@@ -260,3 +260,11 @@ def test_encoders_identical_full_fuzz_corpora(oracle):
             _same_encoders(oracle, np.frombuffer(data, dtype=np.uint8), tag)
             n += 1
     assert n > 900
+
+
+def test_encoders_identical_random_structures(oracle):
+    """The same generator as the GPU fuzz batch (patterns.random_structure), on the CPU: restated
+    amd64 flavour == real assembly, all levels; the streams decode with both decoders."""
+    rng = np.random.default_rng(77)
+    for i in range(250):
+        _same_encoders(oracle, patterns.random_structure(rng, max_n=800000), ("fuzz", i))
