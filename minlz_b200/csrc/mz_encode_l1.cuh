@@ -233,6 +233,27 @@ struct L1AsmBigParams {
     __device__ __forceinline__ uint32_t hash(uint64_t u) const { return hash6(u, 15); }
 };
 
+// LevelSuperFast, Asm flavour, blocks of 64 KiB+1 .. 2 MiB (encodeFastBlockAsm512K / ...2MB:
+// gen.go:70-71: 13 bits, skipLog 5, hash8, step 4; Fast options gen.go:68).
+struct L0AsmBigParams {
+    static constexpr bool kAsm = true;
+    static constexpr bool kMayClamp = false;
+    static constexpr bool kBalanced = false;
+    static constexpr int kMinMatch = 8;
+    static constexpr bool kBackExtend = false;
+    __device__ __forceinline__ int table_bits() const { return 13; }
+    __device__ __forceinline__ int skip_log() const { return 5; }
+    __device__ __forceinline__ int step() const { return 4; }
+    __device__ __forceinline__ int max_fuse_lits() const { return 0; }
+    __device__ __forceinline__ int max_fuse_lits2() const { return 0; }
+    __device__ __forceinline__ int max_fuse_lits3() const { return 0; }
+    __device__ __forceinline__ int s_limit(int n) const { return n - 17; }
+    __device__ __forceinline__ int dst_limit(int n) const { return n - 17 - (n >> 3); }
+    __device__ __forceinline__ int lit_overhead() const { return 4; }
+    __device__ __forceinline__ bool lit_quirk() const { return false; }
+    __device__ __forceinline__ uint32_t hash(uint64_t u) const { return hash8(u, 13); }
+};
+
 // Asm flavour, every other size class of gen.go:57-76 (runtime fields).
 // kMatch8 = the Fast (LevelSuperFast) options: 8-byte compares, hash8, no literal
 // fusing, no backward extension, dstLimit from len>>3 (gen.go:68).
@@ -1077,6 +1098,8 @@ encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
                 res = encode_l1_block(L1AsmBigParams<true>(), dp, sp, n, table, rings[warp], lane, gate, slice);
             else if (!kSuperFast && n > (512 << 10))
                 res = encode_l1_block(L1AsmBigParams<false>(), dp, sp, n, table, rings[warp], lane, gate, slice);
+            else if (kSuperFast && n > (64 << 10) && n <= (2 << 20))
+                res = encode_l1_block(L0AsmBigParams(), dp, sp, n, table, rings[warp], lane, gate, slice);
             else
                 res = encode_l1_block(AsmClassParams<kSuperFast>::for_len(n), dp, sp, n, table, rings[warp], lane, gate,
                                       slice);
