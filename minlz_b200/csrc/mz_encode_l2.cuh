@@ -355,7 +355,18 @@ struct BetterAsmClass {
     }
 };
 
-__device__ int encode_l2_asm_block(const BetterAsmClass P, uint8_t *dst, const uint8_t *src, const int n,
+// The class of the benchmark's block sizes (512 KiB+1 .. 2 MiB, encodeBetterBlockAsm2MB:
+// gen.go:80) with compile-time parameters; every other class runs on the runtime struct above.
+struct BetterAsm2MB {
+    static constexpr int lBits = 17, sBits = 14, skipLog = 7, lHashBytes = 7, maxSkip = 100, outMargin = 17,
+                         inMargin = 17, ovh = 4;
+    static constexpr bool quirk = false, far3 = true, clamp = false;
+    __device__ __forceinline__ uint32_t hashL(uint64_t u) const { return hash7(u, 17); }
+    __device__ __forceinline__ uint32_t hashS(uint64_t u) const { return hash4(u, 14); }
+};
+
+template <class C>
+__device__ int encode_l2_asm_block(const C P, uint8_t *dst, const uint8_t *src, const int n,
                                    uint4 *lTable, uint2 *sTable, uint32_t *rec_mem, const int lane) {
     const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
     L2Records q{rec_mem, 0, 0};
@@ -530,7 +541,9 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
             for (int i = lane; i < (1 << cls.sBits) / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
-            res = encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+            res = (n > (512 << 10) && n <= (2 << 20))
+                      ? encode_l2_asm_block(BetterAsm2MB(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
+                      : encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
