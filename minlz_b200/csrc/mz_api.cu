@@ -298,6 +298,7 @@ struct Workspace {
     uint64_t *h_tab = nullptr;  // pinned mirror of d_tab
     cudaStream_t cs[kMaxChunks] = {};  // chunk pipelines (copy in / kernels / copy out overlap across chunks)
     cudaEvent_t tab_ready = nullptr;
+    cudaEvent_t copied = nullptr;  // sliced upload: the last slice has landed
     int *d_arrived = nullptr;  // arrival gate of the sliced host->device source copy
     int *h_slice_no = nullptr; // pinned 1, 2, 3, ... (source of the gate writes)
 };
@@ -324,6 +325,7 @@ int ws_acquire(int device, Workspace **out) {
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
     for (int c = 0; c < kMaxChunks && e == cudaSuccess; c++) e = cudaStreamCreateWithFlags(&w->cs[c], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->tab_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->copied, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&w->d_arrived, sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_slice_no, kMaxSlices * sizeof(int));
     if (e == cudaSuccess)
@@ -611,7 +613,12 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
                     cudaStreamSynchronize(w->stream);
                     return fail(MZCU_ERR_CUDA, "sliced copy: %s", cudaGetErrorString(ce));
                 }
-                if (crc_out) {  // checksum of the uncompressed blocks, behind the encode = all resident (writer.go:672)
+                // The encode kernel only waits for the bytes it reads: a block that bails out early
+                // (incompressible) lets the launch finish while later slices are still in flight.
+                // The checksum reads, and the pack overwrites, d_src: both must wait for the copy.
+                CU_TRY(cudaEventRecord(w->copied, cp));
+                CU_TRY(cudaStreamWaitEvent(w->stream, w->copied, 0));
+                if (crc_out) {  // checksum of the uncompressed blocks (writer.go:672)
                     rc = launch_crc(device, nblk, w->d_src, d_sbeg, d_send, d_crc, w->stream);
                     if (rc == MZCU_OK)
                         CU_TRY(cudaMemcpyAsync(crc_out, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost,

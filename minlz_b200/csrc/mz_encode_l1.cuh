@@ -350,6 +350,7 @@ __device__ __noinline__ int extend_backward(const uint8_t *src, int cand, int s,
 struct __align__(32) Slot {
     uint4 a, b;
 };
+constexpr int kEncTagSlots = 1 << 15;  // slots per block (the largest table of any class)
 constexpr int kSnapFwd = 24;  // forward bytes held in a slot
 
 // One slot = one 32-byte DRAM sector, moved with Blackwell's 256-bit global
@@ -372,6 +373,33 @@ __device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 
     asm volatile(MZ_SLOT_ST " [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
                  "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                  : "memory");
+}
+
+// ---- tag filter in front of the slots ----------------------------------------
+// A random 32-byte slot read costs a whole 128-byte DRAM line, and only ~45 % of a
+// window's probes can verify at all (profiles/r02_tag_filter_sim.txt).  So every slot
+// has a 4-bit TAG of its 4 verify bytes in a second, dense table: 16 KiB per block,
+// 64 MiB for 4096 blocks in flight -- small enough to live in the 126 MB L2.  A probe
+// reads its tag first (an L2 hit); when the tag differs from the tag of the lane's own
+// 4 bytes the slot's bytes differ too, the probe CANNOT verify, and the DRAM line is
+// never fetched.  A matching tag (the real matches + 1/16 of the rest) fetches the
+// slot and verifies on the bytes as before, so every decision is unchanged.
+// Invariant: tag[h] == tag4(verify bytes of slot h), kept by updating the nibble with
+// one atomic XOR (old ^ new) whenever the slot is overwritten; untouched slots hold
+// position 0, so the table starts as tag4(src[0..4)) everywhere.
+#ifndef MZ_ENC_TAGS
+#define MZ_ENC_TAGS 1
+#endif
+constexpr int kTagWordsPerWarp = kEncTagSlots / 8;  // 8 nibbles per 32-bit word
+__device__ __forceinline__ uint32_t tag4(uint32_t v) { return (v * 2654435761u) >> 28; }
+__device__ __forceinline__ uint32_t tag_load(const uint32_t *p) {
+    uint32_t v;
+    // L1 is bypassed: the nibbles are changed by atomics at L2
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tag_xor(uint32_t *p, uint32_t v) {
+    asm volatile("red.global.xor.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---- per-warp ring of source bytes around the cursor ------------------------
@@ -452,7 +480,7 @@ constexpr int kEncL1Warps = 4;  // warps per CTA
 #define MZ_ENC_L1_MIN_CTAS 7  // 28 warps per SM x 148 SMs >= 4096 blocks in flight, 72 registers
 #endif
 constexpr int kEncL1SlotsPerWarp = 1 << 15;
-constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot);  // 1 MiB
+constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot) + kEncL1SlotsPerWarp / 2;  // 1 MiB + 16 KiB of tags
 
 // 24-bit mask, bit k set when byte k of the two 24-byte strings (6 words each)
 // differs.  Per word: "has non-zero byte" flags at bits 7/15/23/31, gathered
@@ -628,7 +656,7 @@ __device__ __noinline__ uint32_t probe_direct(const uint8_t *src, int n, int pos
 // reference (dstLimit) are evaluated by the token writer with the same values
 // of d, up to 63 records late; the result (0 = incompressible) is the same.
 template <class P>
-__device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, const int n, Slot *table,
+__device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, const int n, Slot *table, uint32_t *tags,
                                uint32_t *ring_mem, const int lane, const int *gate, const int slice) {
     const int sLimit = prm.s_limit(n);
     const int dstLimit = prm.dst_limit(n);
@@ -649,6 +677,13 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         const uint4 ib = make_uint4(w0[3], w0[4], w0[5], w0[6]);
         const int slots = 1 << prm.table_bits();
         for (int i = lane; i < slots; i += 32) slot_store(table + i, ia, ib);
+#if MZ_ENC_TAGS
+        {
+            const uint32_t t0 = tag4(w0[1]) * 0x11111111u;
+            const uint4 tv = make_uint4(t0, t0, t0, t0);
+            for (int i = lane; i < slots / 32; i += 32) reinterpret_cast<uint4 *>(tags)[i] = tv;
+        }
+#endif
         __syncwarp();
     }
 
@@ -689,6 +724,8 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         unsigned rep_sh = 0;
         uint64_t far8 = 0;  // src[p-kClampDist-2 .. +8): the three clamped candidates of this position
         const bool rep_lane = active && p >= repeat;
+        uint32_t tagw = 0, tagx = 0;  // the tag word of this lane's slot; old ^ own nibble (0 = the slot may verify)
+        bool fetched = false;
         if (!done) {
             ring.seek(wbase - 8);
             ring.ensure(min(wbase + 320, fill_limit), lane);
@@ -699,7 +736,11 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             // (:236-239); in search mode the step probes t, t+1, t+2 and whatever follows -- the next
             // step at nextS >= t + step, or the end of a match of >= 4 bytes -- lies at t + step or beyond.
             const bool never = rematch ? lane < 2 : (lane >= 3 && lane < prm.step());
+#if MZ_ENC_TAGS
+            if (active) tagw = tag_load(tags + (h >> 3));
+#else
             if (active && !never) slot_load(table + h, ea, eb);
+#endif
             if (rep_lane) {
                 // (the funnel shift would wait for the load right here: keep the raw words)
                 const uintptr_t ra = reinterpret_cast<uintptr_t>(src + p - repeat);
@@ -712,6 +753,15 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
                 const int lo = p - kClampDist - 2;
                 far8 = lo >= 0 ? ldg_u64_unaligned(src + lo) : ldg_u64_unaligned(src) << (8 * -lo);
             }
+#if MZ_ENC_TAGS
+            // (a far candidate of the 8 MiB Asm class is compared at its CLAMPED position, which the
+            // tag says nothing about: always fetch there)
+            tagx = ((tagw >> ((h & 7u) * 4u)) ^ tag4(W[1])) & 15u;
+            fetched = active && !never && (tagx == 0 || (clamp_far && p >= kClampDist));
+            if (fetched) slot_load(table + h, ea, eb);
+#else
+            fetched = active && !never;
+#endif
         }
 
         // ---------------- the loads are in flight: write queued tokens ----------------
@@ -739,6 +789,9 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             const uint32_t xb = ea.y ^ W[0];
             nz |= (xb ? __clz(xb) >> 3 : 4) << 24;  // back-equal bytes ride in bits 24..26
         }
+#if MZ_ENC_TAGS
+        if (!fetched) nz = 0xffffffu;  // cannot verify; never `cold`
+#endif
         const bool eqm = active && (nz & kMinMask) == 0;
         const int dist = p - cand;
         // search probe j of a step sees minSrcPos = t - maxCopy3Offset (:83): dist <= max + j
@@ -1022,6 +1075,9 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         // ---------------- write back the inserts the replay performed ----------------
         if (((ins >> lane) & 1u) && (same & ins & above) == 0) {  // a later insert on the same slot wins
             slot_store(table + h, make_uint4((uint32_t)p, W[0], W[1], W[2]), make_uint4(W[3], W[4], W[5], W[6]));
+#if MZ_ENC_TAGS
+            if (tagx) tag_xor(tags + (h >> 3), tagx << ((h & 7u) * 4u));
+#endif
         }
         __syncwarp();
     }
@@ -1046,6 +1102,9 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
     const int warp = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
     Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
+    // the tag tables of all warps lie together behind the slots (dense: they are meant to stay in L2)
+    uint32_t *tags = reinterpret_cast<uint32_t *>(tables + (size_t)gridDim.x * kEncL1Warps * kEncL1SlotsPerWarp) +
+                     (size_t)gwarp * kTagWordsPerWarp;
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(counter, 1);
@@ -1058,11 +1117,11 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
         if (n64 >= kMinNonLiteralBlockSize && n64 <= kMaxBlockSize) {
             const int n = (int)n64;
             if (kSuperFast)
-                res = n <= 65536 ? encode_l1_block(L0Params<true>(), dp, sp, n, table, rings[warp], lane, gate, slice)
-                                 : encode_l1_block(L0Params<false>(), dp, sp, n, table, rings[warp], lane, gate, slice);
+                res = n <= 65536 ? encode_l1_block(L0Params<true>(), dp, sp, n, table, tags, rings[warp], lane, gate, slice)
+                                 : encode_l1_block(L0Params<false>(), dp, sp, n, table, tags, rings[warp], lane, gate, slice);
             else
-                res = n <= 65536 ? encode_l1_block(L1Params<true>(), dp, sp, n, table, rings[warp], lane, gate, slice)
-                                 : encode_l1_block(L1Params<false>(), dp, sp, n, table, rings[warp], lane, gate, slice);
+                res = n <= 65536 ? encode_l1_block(L1Params<true>(), dp, sp, n, table, tags, rings[warp], lane, gate, slice)
+                                 : encode_l1_block(L1Params<false>(), dp, sp, n, table, tags, rings[warp], lane, gate, slice);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
@@ -1082,6 +1141,9 @@ encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
     const int warp = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
     Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
+    // the tag tables of all warps lie together behind the slots (dense: they are meant to stay in L2)
+    uint32_t *tags = reinterpret_cast<uint32_t *>(tables + (size_t)gridDim.x * kEncL1Warps * kEncL1SlotsPerWarp) +
+                     (size_t)gwarp * kTagWordsPerWarp;
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(counter, 1);
@@ -1095,14 +1157,14 @@ encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
         if (n64 > (kSuperFast ? 32 : kMinNonLiteralBlockSize) && n64 <= kMaxBlockSize) {
             const int n = (int)n64;
             if (!kSuperFast && n > (2 << 20))
-                res = encode_l1_block(L1AsmBigParams<true>(), dp, sp, n, table, rings[warp], lane, gate, slice);
+                res = encode_l1_block(L1AsmBigParams<true>(), dp, sp, n, table, tags, rings[warp], lane, gate, slice);
             else if (!kSuperFast && n > (512 << 10))
-                res = encode_l1_block(L1AsmBigParams<false>(), dp, sp, n, table, rings[warp], lane, gate, slice);
+                res = encode_l1_block(L1AsmBigParams<false>(), dp, sp, n, table, tags, rings[warp], lane, gate, slice);
             else if (kSuperFast && n > (64 << 10) && n <= (2 << 20))
-                res = encode_l1_block(L0AsmBigParams(), dp, sp, n, table, rings[warp], lane, gate, slice);
+                res = encode_l1_block(L0AsmBigParams(), dp, sp, n, table, tags, rings[warp], lane, gate, slice);
             else
-                res = encode_l1_block(AsmClassParams<kSuperFast>::for_len(n), dp, sp, n, table, rings[warp], lane, gate,
-                                      slice);
+                res = encode_l1_block(AsmClassParams<kSuperFast>::for_len(n), dp, sp, n, table, tags, rings[warp], lane,
+                                      gate, slice);
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();

@@ -168,3 +168,30 @@ def test_config4_shape_stream_roundtrip():
     out = io.BytesIO()
     assert mzs.NewReader(io.BytesIO(blob)).WriteTo(out) == len(data)
     assert out.getvalue() == data
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [1, -1])
+def test_sliced_upload_incompressible_blocks_crc(oracle, level):
+    """Sliced host upload (>= 64 equal blocks of >= 256 KiB): blocks that bail out early
+    let the encode launch finish while later slices are still in flight; the checksum
+    and the pack must still see the whole source (writer.go:672: CRC of the raw block)."""
+    from minlz_b200 import _lib
+    lib = _lib.load()
+    nblk, bs = 96, 1 << 20
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, (nblk, bs), dtype=np.uint8)
+    data[::7, : bs // 2] = 0x41  # a few compressible blocks among the stored ones
+    flat = data.reshape(-1)
+    soff = np.arange(nblk + 1, dtype=np.uint64) * bs
+    for rep in range(2):
+        dst = np.zeros(flat.size + 64, dtype=np.uint8)
+        poff = np.zeros(nblk + 1, dtype=np.uint64)
+        crc = np.zeros(nblk, dtype=np.uint32)
+        r = lib.mzcu_stream_encode_blocks(-1, level, nblk, flat.ctypes.data, soff.ctypes.data, dst.ctypes.data, dst.size,
+                                          poff.ctypes.data, crc.ctypes.data)
+        assert r == 0, lib.mzcu_last_error()
+        for i in range(nblk):
+            assert int(crc[i]) == oracle.crc(data[i].tobytes()), (rep, i)
+        for i in range(0, nblk, 5):
+            assert dst[int(poff[i]):int(poff[i + 1])].tobytes() == oracle.encode_block(data[i], level), (rep, i)
