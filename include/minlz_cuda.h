@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MZCU_ABI_VERSION 1
+#define MZCU_ABI_VERSION 2
 
 /* minlz.go:24 MaxBlockSize */
 #define MZCU_MAX_BLOCK_SIZE (8 << 20)
@@ -51,6 +51,7 @@ extern "C" {
 #define MZCU_ERR_DST_TOO_SMALL (-5) /* C callers must size dst; Go would allocate */
 #define MZCU_ERR_CUDA (-6)          /* CUDA runtime failure / no device; see mzcu_last_error */
 #define MZCU_ERR_INVALID_ARG (-7)
+#define MZCU_ERR_VALIDATE (-8)      /* validate mode: an encoded block did not decode back to its source */
 
 /* decode.go:25-27 decodeErrCodeCorrupt: per-block status of the decode seam */
 #define MZCU_BLOCK_OK 0
@@ -151,6 +152,8 @@ int mzcu_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
  *   source block (what Writer.write needs per block, writer.go:670-696).
  * mzcu_stream_decode_blocks: mzcu_decode_blocks + crc_out[i] of the decoded
  *   block (what Reader.Read checks, reader.go:334-351).  crc_out may be NULL. */
+/* Any block below 4 GiB (the length-combine tables cover every 32-bit length; stream chunks are
+ * below 16 MiB); the host form rejects larger blocks with MZCU_ERR_TOO_LARGE. */
 int mzcu_crc32c_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint32_t *crc, void *stream);
 int mzcu_crc32c_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint32_t *crc);
 int mzcu_stream_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
@@ -178,6 +181,57 @@ int mzcu_encode_batch(int device, int level, int nblk, const uint8_t *src, const
                       const uint64_t *dst_off, uint64_t *enc_len);
 int mzcu_decode_batch(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
                       const uint64_t *dst_off, int64_t *dec_len);
+
+/* ---- several devices behind one call ------------------------------------
+ * replaces: the goroutine fan-out of Writer.EncodeBuffer (writer.go:441-563, one goroutine per
+ * block at :501) and Reader.DecodeConcurrent (reader.go:575-992, :830-859) for a host that owns
+ * several GPUs.  One batch is sharded over `devices[0..ndev)` in stream order -- device k takes
+ * blocks [nblk*k/ndev, nblk*(k+1)/ndev) -- one library thread per device, each bound to its
+ * device's NUMA node; blocks are independent, so nothing is exchanged between devices.
+ *
+ * encode: block i's token stream lands at dst[dst_off_out[i] .. + out_len[i]) (both arrays have
+ *   nblk entries and are OUTPUTS; out_len 0 = not compressible; the ranges of different devices
+ *   are not adjacent).  dst_cap must be >= the total source bytes.  crc_out (nullable) =
+ *   masked CRC-32C of every source block.
+ * decode: block i's token stream is src[src_beg[i] .. + src_len[i]) -- the layout the encode call
+ *   produced -- and decodes into dst[dst_off[i] .. dst_off[i+1]). */
+int mzcu_stream_encode_blocks_multi(int ndev, const int *devices, int level, int nblk, const uint8_t *src,
+                                    const uint64_t *src_off, uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out,
+                                    uint32_t *out_len, uint32_t *crc_out);
+int mzcu_stream_decode_blocks_multi(int ndev, const int *devices, int nblk, const uint8_t *src, const uint64_t *src_beg,
+                                    const uint32_t *src_len, uint8_t *dst, const uint64_t *dst_off, int32_t *status,
+                                    uint32_t *crc_out);
+
+/* ---- asynchronous host calls ----------------------------------------------
+ * The reference's Writer keeps `concurrency` blocks in flight (writer.go:214-272: results are
+ * handed over in order while later blocks still encode).  The batch analogue: submit returns a
+ * job id (> 0) at once; the call runs on a library thread with its own workspace and streams, so
+ * the D2H of batch k overlaps the H2D and kernels of batch k+1.  mzcu_wait blocks, returns the
+ * call's result and retires the job.  All buffers must stay valid until mzcu_wait returns. */
+int64_t mzcu_submit_stream_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
+                                         uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out, uint32_t *crc_out);
+int64_t mzcu_submit_stream_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                                         const uint64_t *dst_off, int32_t *status, uint32_t *crc_out);
+int mzcu_wait(int64_t job);
+
+/* ---- validate mode ----------------------------------------------------------
+ * replaces: debugValidateBlocks (minlz.go:52; encode.go:108-133, writer.go:584-600): every block
+ * the encoder compressed is decoded again ON THE DEVICE and compared with its source before an
+ * encode call returns; a mismatch fails the call with MZCU_ERR_VALIDATE and names the block in
+ * mzcu_last_error.  Off by default; MZCU_VALIDATE=1 in the environment turns it on at start. */
+int mzcu_set_validate(int on);
+int mzcu_get_validate(void);
+/* The validate pass on its own (device pointers, the layout mzcu_encode_blocks_dev produced):
+ * MZCU_OK, or MZCU_ERR_VALIDATE naming the first block that does not decode back to its source.
+ * Synchronises `stream`. */
+int mzcu_validate_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, const uint8_t *enc,
+                             const uint64_t *enc_off, const uint32_t *out_len, void *stream);
+
+/* ---- host placement ---------------------------------------------------------
+ * Binds the calling thread to the CPUs of the NUMA node `device` is attached to and prefers that
+ * node for its later allocations (staging buffers).  Returns the node, or -1 when there is
+ * nothing to bind to (single-node host, no affinity information); never fails the caller. */
+int mzcu_bind_host_to_device(int device);
 
 /* ---- pinned host memory for callers that want fast H2D / D2H ---------- */
 void *mzcu_host_alloc(size_t n);

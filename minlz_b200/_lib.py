@@ -35,6 +35,15 @@ SYMBOLS = {
     "mzcu_host_alloc": (_P, [C.c_size_t]),
     "mzcu_host_free": (None, [_P]),
     "mzcu_last_kernel_ms": (C.c_float, []),
+    "mzcu_stream_encode_blocks_multi": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, _P]),
+    "mzcu_stream_decode_blocks_multi": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "mzcu_submit_stream_encode_blocks": (C.c_int64, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P, _P]),
+    "mzcu_submit_stream_decode_blocks": (C.c_int64, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "mzcu_wait": (C.c_int, [C.c_int64]),
+    "mzcu_set_validate": (C.c_int, [C.c_int]),
+    "mzcu_get_validate": (C.c_int, []),
+    "mzcu_validate_blocks_dev": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "mzcu_bind_host_to_device": (C.c_int, [C.c_int]),
 }
 
 _lib = None

@@ -16,17 +16,38 @@
 #include <mutex>
 #include <vector>
 
-#include "mz_decode.cuh"
 #include "mz_decode_pc.cuh"
 #include "mz_encode_l1.cuh"
 #include "mz_encode_l2.cuh"
 #include "mz_pack.cuh"
 #include "mz_crc32c.cuh"
+#include "mz_validate.cuh"
+
+#include <condition_variable>
+#include <map>
+#include <thread>
+#include <climits>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 namespace {
 
 // Encoder flavour (see minlz_cuda.h): process-wide, like the build tag it stands for.
 std::atomic<int> g_flavor{MZCU_FLAVOR_GO};
+
+// Validate mode (mzcu_set_validate / MZCU_VALIDATE=1): decode-after-encode on the device,
+// the reference's debugValidateBlocks (minlz.go:52, encode.go:108-133).  -1 = read the env once.
+std::atomic<int> g_validate{-1};
+bool validate_on() {
+    int v = g_validate.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("MZCU_VALIDATE");
+        v = (e && *e && *e != '0') ? 1 : 0;
+        g_validate.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
 
 thread_local char g_err[512] = "";
 thread_local float g_last_kernel_ms = 0.f;
@@ -92,7 +113,7 @@ void build_crc_tables(mz::CrcTables *t) {
         uint32_t c = 1u << i;
         t->zeros[0][i] = t->byte_table[c & 0xff] ^ (c >> 8);
     }
-    for (int k = 1; k < 24; k++)  // square the operator
+    for (int k = 1; k < 32; k++)  // square the operator
         for (int i = 0; i < 32; i++) {
             uint32_t v = t->zeros[k - 1][i], r = 0;
             for (int b = 0; b < 32; b++)
@@ -112,6 +133,12 @@ int init_device(int device) {
             const char *g = getenv("MINLZ_CUDA_L2_FETCH");
             const int gran = g ? atoi(g) : kDefaultL2Fetch;
             if (gran > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran) != cudaSuccess)
+                cudaGetLastError();
+        }
+        if (e == cudaSuccess) {
+            // experiment knob: L2 set-aside for persisting (evict_last) lines, in MiB
+            const char *g = getenv("MINLZ_CUDA_L2_PERSIST_MB");
+            if (g && atoi(g) > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(g) << 20) != cudaSuccess)
                 cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaMalloc(&st.counters, kCounterSlots * sizeof(int));
@@ -262,6 +289,53 @@ int launch_pack(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, 
     if (grid > nblk) grid = nblk;
     mz::pack_blocks_kernel<<<grid, 256, 0, stream>>>(nblk, src, sbeg, len, dst, off);
     CU_TRY(cudaGetLastError());
+    return MZCU_OK;
+}
+
+// Validate mode: decodes what the encoder wrote (token streams in their slots: dst + dbeg[i],
+// out_len[i] bytes) with the product decode kernel into a scratch image of the source layout and
+// compares.  Synchronises the stream; a debugging aid, like debugValidateBlocks in the reference.
+int validate_encoded(int device, int nblk, const uint8_t *d_src, const uint64_t *d_sbeg, const uint64_t *d_send,
+                     const uint8_t *d_enc, const uint64_t *d_dbeg, const uint32_t *d_out_len, cudaStream_t stream) {
+    if (nblk == 0) return MZCU_OK;
+    uint64_t span = 0;
+    CU_TRY(cudaMemcpyAsync(&span, d_send + (nblk - 1), sizeof span, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    uint8_t *d_dec = nullptr;
+    uint64_t *d_t = nullptr;
+    int32_t *d_status = nullptr;
+    int *d_first = nullptr;
+    auto cleanup = [&] {
+        cudaFree(d_dec);
+        cudaFree(d_t);
+        cudaFree(d_status);
+        cudaFree(d_first);
+    };
+    cudaError_t e = cudaMalloc(&d_dec, span + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&d_t, 2 * (size_t)nblk * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_status, (size_t)nblk * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_first, sizeof(int));
+    const int none = INT_MAX;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, &none, sizeof(int), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(MZCU_ERR_CUDA, "validate scratch: %s", cudaGetErrorString(e));
+    }
+    mz::validate_ranges_kernel<<<(nblk + 255) / 256, 256, 0, stream>>>(nblk, d_dbeg, d_out_len, d_t, d_t + nblk);
+    int rc = launch_decode(device, nblk, d_enc, d_t, d_t + nblk, d_dec, d_sbeg, d_send, d_status, stream);
+    int first = none;
+    if (rc == MZCU_OK) {
+        int grid = g_dev[device].num_sms * 4;
+        if (grid > nblk) grid = nblk;
+        mz::validate_compare_kernel<<<grid, 256, 0, stream>>>(nblk, d_src, d_sbeg, d_send, d_dec, d_out_len, d_status, d_first);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&first, d_first, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) rc = fail(MZCU_ERR_CUDA, "validate: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    if (rc) return rc;
+    if (first != none) return fail(MZCU_ERR_VALIDATE, "validate: block %d does not decode back to its source", first);
     return MZCU_OK;
 }
 
@@ -515,6 +589,10 @@ int host_encode_blocks(int device, int level, int nblk, const uint8_t *src, cons
     rc = launch_encode(device, level, nblk, w->d_src, d_sbeg, d_send, w->d_dst, d_dbeg, d_out, w->stream);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(w->ev1, w->stream));
+    if (validate_on()) {
+        rc = validate_encoded(device, nblk, w->d_src, d_sbeg, d_send, w->d_dst, d_dbeg, d_out, w->stream);
+        if (rc) return rc;
+    }
     CU_TRY(cudaMemcpyAsync(h_out, d_out, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     CU_TRY(cudaStreamSynchronize(w->stream));
     for (int i = 0; i < nblk; i++) {
@@ -576,7 +654,8 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
     // then costs max(kernel, copy) instead of copy + kernel.
     {
         const size_t B = src_off[1] - src_off[0];
-        bool uniform = level != MZCU_LEVEL_BALANCED && nblk >= 64 && B >= (256u << 10) && B % 128 == 0 && slice_bytes() > 0;
+        bool uniform = level != MZCU_LEVEL_BALANCED && nblk >= 64 && B >= (256u << 10) && B % 128 == 0 && slice_bytes() > 0 &&
+                       !validate_on();
         for (int i = 1; uniform && i < nblk; i++) {
             const size_t n = src_off[i + 1] - src_off[i];
             uniform = i + 1 < nblk ? n == B : (n <= B && n > 0);
@@ -667,6 +746,10 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
         }
         rc = launch_encode(device, level, m, w->d_src, d_sbeg + f, d_send + f, w->d_dst, d_dbeg + f, d_out + f, cs);
         if (rc) return rc;
+        if (validate_on()) {
+            rc = validate_encoded(device, m, w->d_src, d_sbeg + f, d_send + f, w->d_dst, d_dbeg + f, d_out + f, cs);
+            if (rc) return rc;
+        }
         // the chunk's source is dead after its encode: pack into its own source range
         // (sum(len) < chunk bytes); the chunk's offsets start at 0 (own poff slice, stride m+1)
         rc = launch_pack(device, m, w->d_dst, d_dbeg + f, d_out + f, w->d_src + cb, d_poff + f + c, cs);
@@ -801,6 +884,61 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
 
 }  // namespace
 
+// ---- helpers of the multi-device and asynchronous entry points ----
+namespace {
+struct MultiPart {
+    int rc = MZCU_OK;
+    char err[512] = "";
+};
+template <class F>
+int run_on_devices(int ndev, const int *devices, int nblk, F &&call) {
+    if (ndev <= 0 || !devices) return fail(MZCU_ERR_INVALID_ARG, "empty device list");
+    if (ndev > kMaxDevices) return fail(MZCU_ERR_INVALID_ARG, "too many devices");
+    std::vector<MultiPart> part(ndev);
+    std::vector<std::thread> th;
+    for (int k = 0; k < ndev; k++) {
+        const int lo = (int)((int64_t)nblk * k / ndev), hi = (int)((int64_t)nblk * (k + 1) / ndev);
+        if (hi == lo) continue;
+        th.emplace_back([&, k, lo, hi] {
+            mzcu_bind_host_to_device(devices[k]);
+            part[k].rc = call(devices[k], lo, hi);
+            if (part[k].rc) snprintf(part[k].err, sizeof part[k].err, "device %d: %.480s", devices[k], g_err);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int k = 0; k < ndev; k++)
+        if (part[k].rc) return fail(part[k].rc, "%s", part[k].err);
+    return MZCU_OK;
+}
+}  // namespace
+
+namespace {
+struct Job {
+    std::thread th;
+    int rc = MZCU_OK;
+    char err[512] = "";
+};
+std::mutex g_job_mu;
+std::map<int64_t, Job *> g_jobs;
+int64_t g_next_job = 1;
+
+template <class F>
+int64_t submit_job(F &&call) {
+    Job *j = new Job();
+    int bound = -1;
+    cudaGetDevice(&bound);
+    j->th = std::thread([j, call, bound] {
+        if (bound >= 0) cudaSetDevice(bound);
+        j->rc = call();
+        if (j->rc) snprintf(j->err, sizeof j->err, "%s", g_err);
+    });
+    std::lock_guard<std::mutex> lk(g_job_mu);
+    const int64_t id = g_next_job++;
+    g_jobs[id] = j;
+    return id;
+}
+}  // namespace
+
 // ============================ exported C ABI ================================
 extern "C" {
 
@@ -870,7 +1008,10 @@ int mzcu_encode_blocks_dev(int device, int level, int nblk, const uint8_t *src, 
     if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
     int rc = init_device(device);
     if (rc) return rc;
-    return launch_encode(device, level, nblk, src, src_off, src_off + 1, dst, dst_off, out_len, (cudaStream_t)stream);
+    rc = launch_encode(device, level, nblk, src, src_off, src_off + 1, dst, dst_off, out_len, (cudaStream_t)stream);
+    if (rc == MZCU_OK && validate_on())
+        rc = validate_encoded(device, nblk, src, src_off, src_off + 1, dst, dst_off, out_len, (cudaStream_t)stream);
+    return rc;
 }
 
 int mzcu_decode_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
@@ -928,6 +1069,9 @@ int mzcu_crc32c_blocks_dev(int device, int nblk, const uint8_t *src, const uint6
 int mzcu_crc32c_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint32_t *crc) {
     if (nblk < 0 || (nblk > 0 && (!src_off || !crc))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
     if (nblk == 0) return MZCU_OK;
+    for (int i = 0; i < nblk; i++)
+        if (src_off[i + 1] < src_off[i] || src_off[i + 1] - src_off[i] > 0xffffffffull)
+            return fail(MZCU_ERR_TOO_LARGE, "block %d: the checksum kernel takes blocks below 4 GiB", i);
     device = resolve_device(device);
     if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
     int rc = init_device(device);
@@ -1084,6 +1228,163 @@ int64_t mzcu_decode(uint8_t *dst, size_t dst_cap, const uint8_t *block, size_t n
     if (rc) return rc;
     if (dl < 0) return fail((int)dl, "decode failed (%lld)", (long long)dl);
     return dl;
+}
+
+int mzcu_set_validate(int on) {
+    g_validate.store(on ? 1 : 0, std::memory_order_relaxed);
+    return MZCU_OK;
+}
+
+int mzcu_get_validate(void) { return validate_on() ? 1 : 0; }
+
+int mzcu_validate_blocks_dev(int device, int nblk, const uint8_t *src, const uint64_t *src_off, const uint8_t *enc,
+                             const uint64_t *enc_off, const uint32_t *out_len, void *stream) {
+    if (nblk < 0 || (nblk > 0 && (!src || !src_off || !enc || !enc_off || !out_len)))
+        return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    int rc = init_device(device);
+    if (rc) return rc;
+    return validate_encoded(device, nblk, src, src_off, src_off + 1, enc, enc_off, out_len, (cudaStream_t)stream);
+}
+
+// ---- host placement -----------------------------------------------------------
+// Pins the calling thread (and the threads it creates later) to the CPUs of the NUMA node the
+// device hangs off, and prefers that node for its future allocations (pinned staging buffers are
+// first-touched by the thread that allocates them).  Returns the node, or -1 when the platform
+// exposes none / the device has no affinity -- in which case nothing is changed.
+int mzcu_bind_host_to_device(int device) {
+    device = resolve_device(device);
+    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = bus; *c; c++)
+        if (*c >= 'A' && *c <= 'Z') *c += 'a' - 'A';
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0 || node >= 1024) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int a, b, any = 0;
+    for (;;) {  // "0-15,32-47"
+        if (fscanf(f, "%d", &a) != 1) break;
+        b = a;
+        int c = fgetc(f);
+        if (c == '-') {
+            if (fscanf(f, "%d", &b) != 1) break;
+            c = fgetc(f);
+        }
+        for (int k = a; k <= b && k < CPU_SETSIZE; k++) {
+            CPU_SET(k, &set);
+            any = 1;
+        }
+        if (c != ',') break;
+    }
+    fclose(f);
+    if (!any) return -1;
+    sched_setaffinity(0, sizeof set, &set);  // best effort (a container may forbid it)
+#ifdef SYS_set_mempolicy
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8);
+#endif
+    return node;
+}
+
+// ---- several devices behind one call (mzcu_init(ndev, devs)) ----------
+// A Go host cannot use torch.distributed: these entry points shard one batch over a device list
+// inside the library -- contiguous block ranges in stream order (device k gets blocks
+// [nblk*k/ndev, nblk*(k+1)/ndev)), one host thread per device, each running the single-device
+// host call on its range.  Blocks are independent, so there is no exchange between devices.
+
+int mzcu_stream_encode_blocks_multi(int ndev, const int *devices, int level, int nblk, const uint8_t *src,
+                                    const uint64_t *src_off, uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out,
+                                    uint32_t *out_len, uint32_t *crc_out) {
+    if (nblk < 0 || (nblk > 0 && (!src_off || !dst || !dst_off_out || !out_len)))
+        return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    if (nblk == 0) return MZCU_OK;
+    // device k packs its range into the part of dst that mirrors its source range (a packed block
+    // is never longer than its source), so the ranges of different devices cannot collide
+    if (dst_cap < src_off[nblk] - src_off[0]) return fail(MZCU_ERR_DST_TOO_SMALL, "dst_cap < total source bytes");
+    return run_on_devices(ndev, devices, nblk, [&](int dev, int lo, int hi) -> int {
+        const int m = hi - lo;
+        std::vector<uint64_t> off((size_t)m + 1);
+        const size_t base = src_off[lo] - src_off[0];
+        int rc = host_encode_blocks_packed(dev, level, m, src, src_off + lo, dst + base, src_off[hi] - src_off[lo], off.data(),
+                                           crc_out ? crc_out + lo : nullptr);
+        if (rc) return rc;
+        for (int i = 0; i < m; i++) {
+            dst_off_out[lo + i] = base + off[i];
+            out_len[lo + i] = (uint32_t)(off[i + 1] - off[i]);
+        }
+        return MZCU_OK;
+    });
+}
+
+int mzcu_stream_decode_blocks_multi(int ndev, const int *devices, int nblk, const uint8_t *src, const uint64_t *src_beg,
+                                    const uint32_t *src_len, uint8_t *dst, const uint64_t *dst_off, int32_t *status,
+                                    uint32_t *crc_out) {
+    if (nblk < 0 || (nblk > 0 && (!src || !src_beg || !src_len || !dst || !dst_off || !status)))
+        return fail(MZCU_ERR_INVALID_ARG, "null argument");
+    if (nblk == 0) return MZCU_OK;
+    return run_on_devices(ndev, devices, nblk, [&](int dev, int lo, int hi) -> int {
+        const int m = hi - lo;
+        std::vector<uint64_t> sbeg((size_t)m), send((size_t)m);
+        for (int i = 0; i < m; i++) {
+            sbeg[i] = src_beg[lo + i];
+            send[i] = src_beg[lo + i] + src_len[lo + i];
+        }
+        return host_decode_ranges(dev, m, src, sbeg.data(), send.data(), dst, dst_off + lo, dst_off + lo + 1, status + lo,
+                                  crc_out ? crc_out + lo : nullptr);
+    });
+}
+
+// ---- asynchronous host calls ---------------------------------------------------
+// submit returns at once with a job id (> 0); the call runs on a library thread with its own
+// pooled workspace and streams, so the download of call k overlaps the upload and the kernels of
+// call k+1 (PCIe is full duplex).  mzcu_wait blocks until the job is done, returns the call's
+// result (its message is copied to this thread's mzcu_last_error) and retires the job.
+
+int64_t mzcu_submit_stream_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
+                                         uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out, uint32_t *crc_out) {
+    return submit_job([=]() -> int {
+        return host_encode_blocks_packed(device, level, nblk, src, src_off, dst, dst_cap, dst_off_out, crc_out);
+    });
+}
+
+int64_t mzcu_submit_stream_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
+                                         const uint64_t *dst_off, int32_t *status, uint32_t *crc_out) {
+    return submit_job([=]() -> int {
+        if (nblk < 0 || (nblk > 0 && (!src_off || !dst_off || !status))) return fail(MZCU_ERR_INVALID_ARG, "null argument");
+        return host_decode_ranges(device, nblk, src, src_off, src_off + 1, dst, dst_off, dst_off + 1, status, crc_out);
+    });
+}
+
+int mzcu_wait(int64_t job) {
+    Job *j = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_job_mu);
+        auto it = g_jobs.find(job);
+        if (it == g_jobs.end()) return fail(MZCU_ERR_INVALID_ARG, "unknown job %lld", (long long)job);
+        j = it->second;
+        g_jobs.erase(it);
+    }
+    j->th.join();
+    const int rc = j->rc;
+    if (rc) snprintf(g_err, sizeof g_err, "%s", j->err);
+    delete j;
+    return rc;
 }
 
 void *mzcu_host_alloc(size_t n) {

@@ -52,6 +52,15 @@ __device__ __forceinline__ uint64_t ldg_u64_unaligned(const uint8_t *p) {
     return (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
 }
 
+// 8 stream bytes at s (zero filled past slen); never reads a word that holds
+// no byte of [0, slen).
+__device__ __forceinline__ uint64_t ldg_window(const uint8_t *sp, int64_t s, int64_t slen) {
+    if (s + 8 <= slen) return ldg_u64_unaligned(sp + s);
+    uint64_t w = 0;
+    for (int i = 0; i < 8 && s + i < slen; i++) w |= (uint64_t)sp[s + i] << (8 * i);
+    return w;
+}
+
 // hashes: encode_l1.go:26-29, encode_l2.go:25-49
 __device__ __forceinline__ uint32_t hash4(uint64_t u, int h) { return ((uint32_t)u * 2654435761u) >> (32 - h); }
 __device__ __forceinline__ uint32_t hash5(uint64_t u, int h) {

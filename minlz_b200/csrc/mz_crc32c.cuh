@@ -18,7 +18,7 @@ constexpr int kCrcWarps = 8;
 
 struct CrcTables {
     uint32_t byte_table[256];  // reflected Castagnoli table
-    uint32_t zeros[24][32];    // zeros[k][i]: image of register bit i after 2^k zero bytes
+    uint32_t zeros[32][32];    // zeros[k][i]: image of register bit i after 2^k zero bytes (any 32-bit length)
 };
 
 __device__ __forceinline__ uint32_t crc_apply(const uint32_t *m, uint32_t v) {

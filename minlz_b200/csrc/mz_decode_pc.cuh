@@ -38,7 +38,6 @@
 #pragma once
 
 #include "mz_common.cuh"
-#include "mz_decode.cuh"
 
 namespace mz {
 
@@ -419,6 +418,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     // carry the cursor and the repeat offset to the next batch of this block
                     const unsigned defm = __ballot_sync(kFullMask, lane < n && mlen != 0 && !isrep);
                     const uint32_t newoff = defm ? __shfl_sync(kFullMask, off_tok, 31 - __clz(defm)) : off_carry;
+                    __syncwarp();  // every lane has read st->d / st->off / st->dead of this slot
                     if (lane == 0) {
                         st->d[slot] = d_base + total;
                         st->off[slot] = newoff;

@@ -359,7 +359,11 @@ constexpr int kSnapFwd = 24;  // forward bytes held in a slot
 __device__ __forceinline__ void slot_load(const Slot *p, uint4 &a, uint4 &b) {
 #ifndef MZ_SLOT_LD
 // no L1 allocation: a slot is read once per probe and 4.3 GB of tables never fit anyway (-2 %)
+#if MZ_ENC_L2_HINTS
+#define MZ_SLOT_LD "ld.global.L1::no_allocate.L2::evict_first.v8.b32"
+#else
 #define MZ_SLOT_LD "ld.global.L1::no_allocate.v8.b32"
+#endif
 #endif
     asm volatile(MZ_SLOT_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
@@ -368,7 +372,11 @@ __device__ __forceinline__ void slot_load(const Slot *p, uint4 &a, uint4 &b) {
 }
 __device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 &b) {
 #ifndef MZ_SLOT_ST
+#if MZ_ENC_L2_HINTS
+#define MZ_SLOT_ST "st.global.L2::evict_first.v8.b32"
+#else
 #define MZ_SLOT_ST "st.global.v8.b32"
+#endif
 #endif
     asm volatile(MZ_SLOT_ST " [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
                  "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
@@ -384,22 +392,54 @@ __device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 
 // 4 bytes the slot's bytes differ too, the probe CANNOT verify, and the DRAM line is
 // never fetched.  A matching tag (the real matches + 1/16 of the rest) fetches the
 // slot and verifies on the bytes as before, so every decision is unchanged.
-// Invariant: tag[h] == tag4(verify bytes of slot h), kept by updating the nibble with
+// Invariant: tag[h] == tag_of(verify bytes of slot h), kept by updating the nibble with
 // one atomic XOR (old ^ new) whenever the slot is overwritten; untouched slots hold
-// position 0, so the table starts as tag4(src[0..4)) everywhere.
+// position 0, so the table starts as tag_of(src[0..4)) everywhere.
+// MZ_ENC_TAGS: 0 = no filter, 1 = tags in global memory / L2 (MZ_ENC_TAG_BITS wide), 2 = 1-bit tags in
+// shared memory (4 KiB per block: no extra memory traffic and no dependent L2 round trip, half the power)
 #ifndef MZ_ENC_TAGS
 #define MZ_ENC_TAGS 1
 #endif
-constexpr int kTagWordsPerWarp = kEncTagSlots / 8;  // 8 nibbles per 32-bit word
-__device__ __forceinline__ uint32_t tag4(uint32_t v) { return (v * 2654435761u) >> 28; }
+#ifndef MZ_ENC_TAG_BITS
+#define MZ_ENC_TAG_BITS 4
+#endif
+#if MZ_ENC_TAGS == 2
+#undef MZ_ENC_TAG_BITS
+#define MZ_ENC_TAG_BITS 1
+#endif
+#ifndef MZ_ENC_L2_HINTS
+#define MZ_ENC_L2_HINTS 1  // tags: L2 evict_last; slots: L2 evict_first (streamed once, 4.3 GB of them)
+#endif
+constexpr int kTagBits = MZ_ENC_TAG_BITS;
+constexpr int kTagsPerWord = 32 / kTagBits;
+constexpr uint32_t kTagMask = (1u << kTagBits) - 1u;
+constexpr int kTagWordsPerWarp = kEncTagSlots / kTagsPerWord;
+__device__ __forceinline__ uint32_t tag_of(uint32_t v) { return (v * 2654435761u) >> (32 - kTagBits); }
+__device__ __forceinline__ uint32_t tag_word_index(uint32_t h) { return h / kTagsPerWord; }
+__device__ __forceinline__ uint32_t tag_shift(uint32_t h) { return (h % kTagsPerWord) * kTagBits; }
 __device__ __forceinline__ uint32_t tag_load(const uint32_t *p) {
     uint32_t v;
-    // L1 is bypassed: the nibbles are changed by atomics at L2
+#if MZ_ENC_TAGS == 2
+    v = *reinterpret_cast<const volatile uint32_t *>(p);
+#elif MZ_ENC_L2_HINTS
+    // L1 is bypassed (.cg): the tags are changed by atomics at L2
+    asm volatile("{\n .reg .b64 pol;\n createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n"
+                 " ld.global.cg.L2::cache_hint.u32 %0, [%1], pol;\n}"
+                 : "=r"(v) : "l"(p) : "memory");
+#else
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ void tag_xor(uint32_t *p, uint32_t v) {
+#if MZ_ENC_TAGS == 2
+    atomicXor(p, v);
+#elif MZ_ENC_L2_HINTS
+    asm volatile("{\n .reg .b64 pol;\n createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n"
+                 " red.global.xor.L2::cache_hint.b32 [%0], %1, pol;\n}" ::"l"(p), "r"(v) : "memory");
+#else
     asm volatile("red.global.xor.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 
 // ---- per-warp ring of source bytes around the cursor ------------------------
@@ -480,7 +520,7 @@ constexpr int kEncL1Warps = 4;  // warps per CTA
 #define MZ_ENC_L1_MIN_CTAS 7  // 28 warps per SM x 148 SMs >= 4096 blocks in flight, 72 registers
 #endif
 constexpr int kEncL1SlotsPerWarp = 1 << 15;
-constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot) + kEncL1SlotsPerWarp / 2;  // 1 MiB + 16 KiB of tags
+constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot) + kTagWordsPerWarp * 4;  // 1 MiB of slots + the tags
 
 // 24-bit mask, bit k set when byte k of the two 24-byte strings (6 words each)
 // differs.  Per word: "has non-zero byte" flags at bits 7/15/23/31, gathered
@@ -679,9 +719,11 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         for (int i = lane; i < slots; i += 32) slot_store(table + i, ia, ib);
 #if MZ_ENC_TAGS
         {
-            const uint32_t t0 = tag4(w0[1]) * 0x11111111u;
+            uint32_t t0 = tag_of(w0[1]);
+#pragma unroll
+            for (int b = kTagBits; b < 32; b <<= 1) t0 |= t0 << b;
             const uint4 tv = make_uint4(t0, t0, t0, t0);
-            for (int i = lane; i < slots / 32; i += 32) reinterpret_cast<uint4 *>(tags)[i] = tv;
+            for (int i = lane; i < slots / kTagsPerWord / 4; i += 32) reinterpret_cast<uint4 *>(tags)[i] = tv;
         }
 #endif
         __syncwarp();
@@ -737,7 +779,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
             // step at nextS >= t + step, or the end of a match of >= 4 bytes -- lies at t + step or beyond.
             const bool never = rematch ? lane < 2 : (lane >= 3 && lane < prm.step());
 #if MZ_ENC_TAGS
-            if (active) tagw = tag_load(tags + (h >> 3));
+            if (active) tagw = tag_load(tags + tag_word_index(h));
 #else
             if (active && !never) slot_load(table + h, ea, eb);
 #endif
@@ -756,7 +798,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
 #if MZ_ENC_TAGS
             // (a far candidate of the 8 MiB Asm class is compared at its CLAMPED position, which the
             // tag says nothing about: always fetch there)
-            tagx = ((tagw >> ((h & 7u) * 4u)) ^ tag4(W[1])) & 15u;
+            tagx = ((tagw >> tag_shift(h)) ^ tag_of(W[1])) & kTagMask;
             fetched = active && !never && (tagx == 0 || (clamp_far && p >= kClampDist));
             if (fetched) slot_load(table + h, ea, eb);
 #else
@@ -1076,7 +1118,7 @@ __device__ int encode_l1_block(const P prm, uint8_t *dst, const uint8_t *src, co
         if (((ins >> lane) & 1u) && (same & ins & above) == 0) {  // a later insert on the same slot wins
             slot_store(table + h, make_uint4((uint32_t)p, W[0], W[1], W[2]), make_uint4(W[3], W[4], W[5], W[6]));
 #if MZ_ENC_TAGS
-            if (tagx) tag_xor(tags + (h >> 3), tagx << ((h & 7u) * 4u));
+            if (tagx) tag_xor(tags + tag_word_index(h), tagx << tag_shift(h));
 #endif
         }
         __syncwarp();
@@ -1103,8 +1145,13 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
     Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
     // the tag tables of all warps lie together behind the slots (dense: they are meant to stay in L2)
+#if MZ_ENC_TAGS == 2
+    __shared__ uint32_t tag_mem[kEncL1Warps][kTagWordsPerWarp];
+    uint32_t *tags = tag_mem[warp];
+#else
     uint32_t *tags = reinterpret_cast<uint32_t *>(tables + (size_t)gridDim.x * kEncL1Warps * kEncL1SlotsPerWarp) +
                      (size_t)gwarp * kTagWordsPerWarp;
+#endif
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(counter, 1);
@@ -1142,8 +1189,13 @@ encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
     Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
     // the tag tables of all warps lie together behind the slots (dense: they are meant to stay in L2)
+#if MZ_ENC_TAGS == 2
+    __shared__ uint32_t tag_mem[kEncL1Warps][kTagWordsPerWarp];
+    uint32_t *tags = tag_mem[warp];
+#else
     uint32_t *tags = reinterpret_cast<uint32_t *>(tables + (size_t)gridDim.x * kEncL1Warps * kEncL1SlotsPerWarp) +
                      (size_t)gwarp * kTagWordsPerWarp;
+#endif
     for (;;) {
         int blk = 0;
         if (lane == 0) blk = atomicAdd(counter, 1);

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert sorted(_lib.SYMBOLS) == names, "python binding and header disagree"
-    assert lib.mzcu_abi_version() == 1
+    assert lib.mzcu_abi_version() == 2
 
 
 def test_encoder_flavour_setting():
