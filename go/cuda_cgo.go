@@ -17,12 +17,19 @@ import "C"
 
 import (
 	"errors"
+	"runtime"
+	"sync"
 	"unsafe"
 )
 
 var errCuda = errors.New("minlz: cuda backend failure")
 
-func cudaErr(rc C.int) error {
+// call runs one C entry point and, on failure, fetches its message.  The message is
+// thread-local in the library, so the goroutine stays on its OS thread for both calls.
+func call(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	rc := f()
 	switch rc {
 	case C.MZCU_OK:
 		return nil
@@ -48,7 +55,41 @@ const (
 )
 
 // SetEncoderFlavor is process-wide, like the build tag it stands for.
-func SetEncoderFlavor(f int) error { return cudaErr(C.mzcu_set_encoder_flavor(C.int(f))) }
+func SetEncoderFlavor(f int) error {
+	return call(func() C.int { return C.mzcu_set_encoder_flavor(C.int(f)) })
+}
+
+// SetValidate turns on decode-after-encode on the device (debugValidateBlocks, minlz.go:52).
+func SetValidate(on bool) {
+	v := C.int(0)
+	if on {
+		v = 1
+	}
+	C.mzcu_set_validate(v)
+}
+
+// cudaDevices is the device list every batch call shards over (stream order =
+// list order).  Default: device 0.  SetDevices([]int{0,1,...,7}) uses a whole box.
+var (
+	devMu       sync.RWMutex
+	cudaDevices = []C.int{0}
+)
+
+func SetDevices(devs []int) {
+	d := make([]C.int, len(devs))
+	for i, v := range devs {
+		d[i] = C.int(v)
+	}
+	devMu.Lock()
+	cudaDevices = d
+	devMu.Unlock()
+}
+
+func devices() []C.int {
+	devMu.RLock()
+	defer devMu.RUnlock()
+	return cudaDevices
+}
 
 func bptr(b []byte) *C.uint8_t {
 	if len(b) == 0 {
@@ -57,27 +98,74 @@ func bptr(b []byte) *C.uint8_t {
 	return (*C.uint8_t)(unsafe.Pointer(unsafe.SliceData(b)))
 }
 
-// EncodeBlocks runs encodeBlock / encodeBlockBetter over a batch with one GPU
-// launch.  src holds the blocks back to back, srcOff has len(blocks)+1 entries.
-// The token streams come back packed in dst with their offsets; an empty range
-// means "not compressible" exactly like a 0 return of encodeBlock.
-func EncodeBlocks(dst, src []byte, srcOff []uint64, level int) (dstOff []uint64, err error) {
-	n := len(srcOff) - 1
-	dstOff = make([]uint64, n+1)
-	rc := C.mzcu_encode_blocks_packed(-1, C.int(level), C.int(n), bptr(src),
-		(*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(srcOff))), bptr(dst), C.size_t(len(dst)),
-		(*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(dstOff))))
-	return dstOff, cudaErr(rc)
+func u64ptr(b []uint64) *C.uint64_t { return (*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(b))) }
+func u32ptr(b []uint32) *C.uint32_t { return (*C.uint32_t)(unsafe.Pointer(unsafe.SliceData(b))) }
+
+// ---- pinned staging buffers (mzcu_host_alloc), pooled by capacity class ----
+//
+// H2D / D2H from pageable Go memory is staged by the driver at half the speed;
+// batch callers copy their blocks into one of these instead (they are C memory,
+// so cgo's pointer rules do not apply to them either).
+type pinned struct {
+	b []byte
 }
 
-// DecodeBlocks runs minLZDecode over a batch with one GPU launch; status[i] is
-// the reference's return code (0 ok, 1 = decodeErrCodeCorrupt).
-func DecodeBlocks(dst []byte, dstOff []uint64, src []byte, srcOff []uint64) (status []int32, err error) {
+var pinnedPool sync.Map // capacity class (log2) -> *sync.Pool
+
+func getPinned(n int) *pinned {
+	cls := 20 // 1 MiB minimum
+	for (1 << cls) < n {
+		cls++
+	}
+	p, _ := pinnedPool.LoadOrStore(cls, &sync.Pool{})
+	if v := p.(*sync.Pool).Get(); v != nil {
+		return v.(*pinned)
+	}
+	ptr := C.mzcu_host_alloc(C.size_t(1 << cls))
+	if ptr == nil {
+		panic("minlz: mzcu_host_alloc failed") // out of pinned memory: there is no pageable fallback
+	}
+	return &pinned{b: unsafe.Slice((*byte)(ptr), 1<<cls)}
+}
+
+func putPinned(p *pinned) {
+	cls := 0
+	for (1 << cls) < cap(p.b) {
+		cls++
+	}
+	pool, _ := pinnedPool.LoadOrStore(cls, &sync.Pool{})
+	pool.(*sync.Pool).Put(p)
+}
+
+// EncodeBlocks runs encodeBlock / encodeBlockBetter / encodeBlockFast over a batch with
+// one call, sharded over the device list.  src holds the blocks back to back, srcOff has
+// len(blocks)+1 entries.  Block i's token stream is dst[dstOff[i] : dstOff[i]+outLen[i]];
+// outLen 0 means "not compressible" exactly like a 0 return of encodeBlock.  crc[i] is
+// the masked CRC-32C of block i (what the stream writer stores, writer.go:672).
+func EncodeBlocks(dst, src []byte, srcOff []uint64, level int) (dstOff []uint64, outLen, crc []uint32, err error) {
 	n := len(srcOff) - 1
+	dstOff = make([]uint64, n)
+	outLen = make([]uint32, n)
+	crc = make([]uint32, n)
+	devs := devices()
+	err = call(func() C.int {
+		return C.mzcu_stream_encode_blocks_multi(C.int(len(devs)), &devs[0], C.int(level), C.int(n), bptr(src),
+			u64ptr(srcOff), bptr(dst), C.size_t(len(dst)), u64ptr(dstOff), u32ptr(outLen), u32ptr(crc))
+	})
+	return
+}
+
+// DecodeBlocks runs minLZDecode over a batch with one call; status[i] is the reference's
+// return code (0 ok, 1 = decodeErrCodeCorrupt); crc[i] the masked CRC-32C of the decoded
+// block (reader.go:341-351).
+func DecodeBlocks(dst []byte, dstOff []uint64, src []byte, srcBeg []uint64, srcLen []uint32) (status []int32, crc []uint32, err error) {
+	n := len(srcBeg)
 	status = make([]int32, n)
-	rc := C.mzcu_decode_blocks(-1, C.int(n), bptr(src),
-		(*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(srcOff))), bptr(dst),
-		(*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(dstOff))),
-		(*C.int32_t)(unsafe.Pointer(unsafe.SliceData(status))))
-	return status, cudaErr(rc)
+	crc = make([]uint32, n)
+	devs := devices()
+	err = call(func() C.int {
+		return C.mzcu_stream_decode_blocks_multi(C.int(len(devs)), &devs[0], C.int(n), bptr(src), u64ptr(srcBeg),
+			u32ptr(srcLen), bptr(dst), u64ptr(dstOff), (*C.int32_t)(unsafe.Pointer(unsafe.SliceData(status))), u32ptr(crc))
+	})
+	return
 }

@@ -28,6 +28,14 @@
 //     whose source lies inside the span being assembled are applied afterwards
 //     in stream order, warp-cooperatively (overlapping copies replicate the
 //     `offset`-byte pattern).
+//   * LEXER warps take everything off the parser's chain that is not the chain itself.  Where
+//     the next token starts depends on the previous token, but how long a token WOULD be if
+//     one started at byte i depends on bytes i, i+1 only: the lexers prefetch every slot's
+//     stream into a shared-memory ring (coalesced 16-byte cp.async, 32 lanes per slot) and
+//     fill adv[i] for every byte offset of it, lanes in parallel.  The parser's step is then
+//     i += adv[i] -- one shared-memory load -- plus the descriptor stores (~45 cycles per
+//     token instead of ~350).  Extended lengths (adv 0) and bytes not lexed yet take the
+//     parser's old path.
 //   * parser and copiers run bulk-synchronously: round r+1 is parsed while
 //     round r is copied (double-buffered descriptors, one __syncthreads per
 //     round), so there is no fine-grained inter-warp signalling.
@@ -43,10 +51,8 @@ namespace mz {
 
 constexpr int kDecSlots = 32;      // block slots per CTA (one parser lane each)
 constexpr int kDecCopiers = 28;    // copier warps per CTA
-// Warp w runs on scheduler w % 4.  The parser (warp 0) is the serial pole of the CTA, so it
-// gets scheduler 0 to itself: warps 4, 8, 12, ... only wait at the round barrier.
-constexpr bool kDecParserAlone = 1 + kDecCopiers + (kDecCopiers + 2) / 3 <= 32;
-constexpr int kDecWarps = kDecParserAlone ? 1 + kDecCopiers + (kDecCopiers + 2) / 3 : 1 + kDecCopiers;
+constexpr int kDecLexers = 3;      // lexer warps per CTA (stream prefetch + token lengths for the parser)
+constexpr int kDecWarps = 1 + kDecCopiers + kDecLexers;
 constexpr int kDecThreads = kDecWarps * 32;
 constexpr int kDecTok = 32;        // tokens per batch
 constexpr int kDecShort = 40;      // max literal / match length of a "short" token
@@ -54,8 +60,8 @@ constexpr int kDecStage = kDecTok * 2 * kDecShort + 32;       // output image of
 constexpr int kDecLitStage = kDecTok * (8 + kDecShort) + 48;  // stream span of a batch
 constexpr int kDecScratch = 32 * 48 + 16;                     // per-lane 48-byte gather landing zone
 constexpr int kDescStride = 3 * kDecTok + 1;                  // words per (slot, buffer); odd -> conflict free
-constexpr int kDecRing = 1024;                                // per-slot ring of compressed bytes for the parser
-constexpr int kDecRingAhead = 768;                            // bytes kept loaded ahead of the cursor
+constexpr int kDecRing = 512;                                 // per-slot ring of compressed bytes (+ as many token lengths)
+constexpr int kDecRingAhead = 496;                            // bytes kept requested ahead of the cursor
 
 constexpr uint32_t kBatchLong = 0x100;   // the batch is a single long token
 constexpr uint32_t kBatchEnded = 0x200;  // the stream ended behind this batch (decode.go:615 check is due)
@@ -69,11 +75,20 @@ struct DecSlotState {
     // owned by the copier warp of the slot: output cursor, repeat offset, failed
     uint32_t d[kDecSlots], off[kDecSlots], dead[kDecSlots];
     uint8_t lut[256];  // first token byte -> header + literal bytes (bit 7: needs the slow path)
+    // lexer state, one entry per slot, owned by the slot's lexer warp; positions are relative to
+    // lx_abase, the 16-byte aligned address at or below the stream start (a = lead + s)
+    unsigned long long lx_abase[kDecSlots];
+    int lx_lead[kDecSlots], lx_aend[kDecSlots];
+    int lx_fill[kDecSlots];          // requested up to here
+    int lx_done[kDecSlots];          // token lengths written up to here
+    // published to the parser, double buffered by round parity
+    int lx_ready[2][kDecSlots];      // ring bytes below this have landed
+    int lx_lexed[2][kDecSlots];      // adv[] entries below this are valid
 };
 
 constexpr size_t kDecSmemBytes = sizeof(uint32_t) * 2 * kDecSlots * kDescStride + sizeof(DecSlotState) +
                                  (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch) +
-                                 (size_t)kDecSlots * kDecRing + 64;
+                                 (size_t)kDecSlots * kDecRing * 2 + 64;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -222,7 +237,6 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
     DecSlotState *st = reinterpret_cast<DecSlotState *>(desc + 2 * kDecSlots * kDescStride);
     uint8_t *copier_mem = reinterpret_cast<uint8_t *>(st + 1);
     copier_mem += (16 - (reinterpret_cast<uintptr_t>(copier_mem) & 15)) & 15;
-    uint8_t *rings = copier_mem + (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch);  // [kDecSlots][kDecRing]
     __shared__ int produced[2];  // produced[r & 1]: the parser emitted something in round r
 
     const int lane = lane_id();
@@ -231,30 +245,38 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
     const int nslots = min(slots_per_cta, nblk - first_blk);
 
     // ---- parser lane state (warp 0) ----
-    // The parser reads its stream through a per-lane shared-memory ring that is
-    // refilled one round ahead with cp.async, so a step never waits on DRAM
-    // (with 28+ lanes in lockstep, some lane would miss the cache on every step).
-    // Ring positions are relative to `p_abase`, the 16-byte aligned address at or
-    // below the stream start: a = lead + s.
+    // The parser reads its stream and the token lengths through per-slot shared-memory rings
+    // kept filled by the lexer warps (a step never waits on DRAM: with 28 lanes in lockstep
+    // some lane would miss the cache on every step).  Ring positions are relative to the
+    // 16-byte aligned address at or below the stream start: a = lead + s.
+    uint8_t *rings = copier_mem + (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch);  // [kDecSlots][kDecRing]
+    uint8_t *advs = rings + (size_t)kDecSlots * kDecRing;                                          // [kDecSlots][kDecRing]
     const uint8_t *p_sp = nullptr;
     int p_slen = 0, p_s = 0;
     bool p_done = true;
-    uintptr_t p_abase = 0;
-    int p_lead = 0;
-    int p_afill = 0, p_aend = 0, p_ready = 0;  // requested up to afill, landed up to ready, stream ends at aend
-    uint8_t *p_ring = rings + (size_t)lane * kDecRing;
+    int p_lead = 0, p_aend = 0;
+    const uint8_t *p_ring = rings + (size_t)lane * kDecRing;
+    const uint8_t *p_adv = advs + (size_t)lane * kDecRing;
     if (warp == 0 && lane < nslots) {
         const int b = first_blk + lane;
         p_sp = src + sbeg[b];
         p_slen = (int)(send[b] - sbeg[b]);
         p_done = false;
-        p_abase = reinterpret_cast<uintptr_t>(p_sp) & ~uintptr_t(15);
-        p_lead = (int)(reinterpret_cast<uintptr_t>(p_sp) - p_abase);
+        const uintptr_t abase = reinterpret_cast<uintptr_t>(p_sp) & ~uintptr_t(15);
+        p_lead = (int)(reinterpret_cast<uintptr_t>(p_sp) - abase);
         p_aend = p_lead + p_slen;
+        st->lx_abase[lane] = abase;
+        st->lx_lead[lane] = p_lead;
+        st->lx_aend[lane] = p_aend;
+        st->lx_fill[lane] = 0;
+        st->lx_done[lane] = 0;
+        st->lx_ready[0][lane] = st->lx_ready[1][lane] = 0;
+        st->lx_lexed[0][lane] = st->lx_lexed[1][lane] = 0;
     }
     if (threadIdx.x < 256) st->lut[threadIdx.x] = dec_lut_entry(threadIdx.x);
     if (threadIdx.x < kDecSlots) {
         st->count[0][threadIdx.x] = st->count[1][threadIdx.x] = 0;
+        st->s_end[0][threadIdx.x] = st->s_end[1][threadIdx.x] = 0;
         st->d[threadIdx.x] = 0;
         st->off[threadIdx.x] = 1;  // decode.go:186
         st->dead[threadIdx.x] = 0;
@@ -267,17 +289,9 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
         if (warp == 0) {
             // ================= PARSER =================
             uint32_t *my = desc + (wb * kDecSlots + lane) * kDescStride;
-            // what was requested last round has landed; request the next stretch
-            cp_async_wait_all();
-            if (!p_done) {
-                const int apos = p_lead + p_s;
-                if (p_afill < (apos & ~15)) p_afill = apos & ~15;  // a long literal run skipped ahead
-                p_ready = p_afill;
-                while (p_afill < p_aend && p_afill - apos < kDecRingAhead) {
-                    cp_async16(p_ring + (p_afill & (kDecRing - 1)), reinterpret_cast<const void *>(p_abase + (uintptr_t)p_afill));
-                    p_afill += 16;
-                }
-            }
+            // what the lexers published at the end of the previous round
+            const int p_ready = lane < nslots ? st->lx_ready[rb][lane] : 0;
+            const int p_lexed = lane < nslots ? st->lx_lexed[rb][lane] : 0;
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(p_ring);
             auto ring_ok_at = [&](int ap) { return ap + 8 <= p_ready || p_aend <= p_ready; };
             auto ring_load = [&](int ap) {
@@ -297,35 +311,36 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 p_done = true;
                 flags = kBatchEnded;
             }
-            uint64_t w8 = ring_load(p_lead + p_s);
-            bool w_ok = ring_ok_at(p_lead + p_s);
             // One token per lane per step.  No votes and no warp-level early exits in here:
             // every instruction on this path is paid by every block of the CTA on every
-            // token.  Rare cases (bytes not yet in the ring, extended lengths) are plain
-            // divergent branches.
+            // token.  The chain is  a -> adv[a] -> a + adv;  rare cases (bytes not lexed
+            // yet, extended lengths) are plain divergent branches.
 #pragma unroll 2
             for (int k = 0; k < kDecTok; k++) {
                 const bool live = !p_done && !cut && p_s < p_slen;
-                if (live && !w_ok) w8 = ldg_window(p_sp, p_s, p_slen);  // first round / after a long literal run
-                const uint32_t lo = (uint32_t)w8;
-                const uint32_t e = st->lut[lo & 0xff];
-                int adv = (int)(e & 0x7f);
+                const int a = p_lead + p_s;
+                int adv = 0;
+                if (live && a < p_lexed) adv = p_adv[a & (kDecRing - 1)];
+                uint64_t w8 = ring_load(a);  // the descriptor's header bytes (valid below p_lexed)
                 bool lng = false;
-                if (live && ((e & 0x80) != 0 || ((lo & 7) == 7 && ((lo >> 5) & 63) > 60))) {  // extended length
-                    const PTok t = parse_token_bf(w8);
-                    adv = (int)(t.hdr + t.lit);
-                    lng = t.lit > kDecShort || t.mlen > kDecShort;
+                if (live && adv == 0) {  // not lexed yet, or a token the lexers leave to this path
+                    if (!ring_ok_at(a)) w8 = ldg_window(p_sp, p_s, p_slen);  // first rounds / after a long literal run
+                    const uint32_t lo = (uint32_t)w8;
+                    const uint32_t e = st->lut[lo & 0xff];
+                    adv = (int)(e & 0x7f);
+                    if ((e & 0x80) != 0 || ((lo & 7) == 7 && ((lo >> 5) & 63) > 60)) {  // extended length
+                        const PTok t = parse_token_bf(w8);
+                        adv = (int)(t.hdr + t.lit);
+                        lng = t.lit > kDecShort || t.mlen > kDecShort;
+                    }
                 }
                 // header and literals must lie inside the stream (decode.go:221,410 src side)
                 const bool bad = adv > p_slen - p_s;
                 const bool defer = lng && cnt > 0;  // a long token travels alone: it starts the next batch
                 const bool emit = live && !bad && !defer;
-                const int s_next = p_s + adv;
-                const uint64_t w8n = ring_load(p_lead + s_next);  // speculative: used only if emitted
-                const bool wn_ok = ring_ok_at(p_lead + s_next);
                 if (emit) {
                     my[0 * kDecTok + cnt] = (uint32_t)p_s;
-                    my[1 * kDecTok + cnt] = lo;
+                    my[1 * kDecTok + cnt] = (uint32_t)w8;
                     my[2 * kDecTok + cnt] = (uint32_t)(w8 >> 32);
                 }
                 if (live && bad) {
@@ -334,10 +349,8 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 }
                 if (emit && lng) flags |= kBatchLong;
                 cut = cut || (live && !bad && lng);
-                p_s = emit ? s_next : p_s;
+                p_s = emit ? p_s + adv : p_s;
                 cnt += emit ? 1 : 0;
-                w8 = emit ? w8n : w8;
-                w_ok = emit ? wn_ok : w_ok;
             }
             st->count[wb][lane] = (uint32_t)cnt | flags;
             st->s_first[wb][lane] = s_first;
@@ -346,9 +359,48 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             // every block of this CTA is finished
             const bool some = __any_sync(kFullMask, cnt > 0 || flags != 0);
             if (lane == 0) produced[wb] = some ? 1 : 0;
-        } else if (round > 0 && (!kDecParserAlone || ((warp & 3) != 0 && warp - 1 - (warp >> 2) < kDecCopiers))) {
+        } else if (warp > kDecCopiers) {
+            // ================= LEXERS =================
+            cp_async_wait_all();  // what this warp requested in earlier rounds has landed
+            __syncwarp();
+            for (int slot = warp - 1 - kDecCopiers; slot < nslots; slot += kDecLexers) {
+                const int lead = st->lx_lead[slot], aend = st->lx_aend[slot];
+                int afill = st->lx_fill[slot], done = st->lx_done[slot];
+                uint8_t *ring = rings + (size_t)slot * kDecRing;
+                uint8_t *adv = advs + (size_t)slot * kDecRing;
+                const int ready = afill;  // everything requested so far has landed (wait_all above)
+                // the parser's cursor as of the end of the previous round: bytes before it are dead
+                // (their ring cells get reused), so neither lex nor keep them
+                const int cur = lead + (int)st->s_end[rb][slot];
+                if (done < (cur & ~15)) done = cur & ~15;
+                // 1. token lengths of the bytes that have landed.  An entry needs bytes i, i+1; the
+                //    parser also takes the 8 descriptor bytes of a lexed token from the ring, so the
+                //    frontier stays 8 bytes behind what has landed (or reaches the stream's end).
+                const int lim = afill >= aend ? aend : afill - 8;
+                for (int i = done + lane; i < lim; i += 32) {
+                    const uint32_t b0 = ring[i & (kDecRing - 1)], b1 = ring[(i + 1) & (kDecRing - 1)];
+                    uint32_t e = st->lut[b0];
+                    if ((e & 0x80) != 0 || ((b0 & 7) == 7 && (((b0 | b1 << 8) >> 5) & 63) > 60)) e = 0;  // extended: parser's path
+                    adv[i & (kDecRing - 1)] = (uint8_t)e;
+                }
+                if (lim > done) done = lim;
+                // 2. request the next stretch ahead of the cursor
+                if (afill < (cur & ~15)) afill = cur & ~15;  // a long literal run skipped ahead of everything requested
+                const int want = min((aend + 15) & ~15, (cur + kDecRingAhead) & ~15);
+                const int chunk = afill + 16 * lane;
+                if (chunk < want) cp_async16(ring + (chunk & (kDecRing - 1)), reinterpret_cast<const void *>((uintptr_t)st->lx_abase[slot] + (uintptr_t)chunk));
+                if (want > afill) afill = min(want, afill + 16 * 32);
+                __syncwarp();
+                if (lane == 0) {
+                    st->lx_fill[slot] = afill;
+                    st->lx_done[slot] = done;
+                    st->lx_ready[wb][slot] = ready;
+                    st->lx_lexed[wb][slot] = done;
+                }
+            }
+        } else if (round > 0) {
             // ================= COPIERS =================
-            const int cw = kDecParserAlone ? warp - 1 - (warp >> 2) : warp - 1;
+            const int cw = warp - 1;
             uint8_t *stage = copier_mem + (size_t)cw * (kDecStage + kDecLitStage + kDecScratch);
             uint8_t *lstage = stage + kDecStage;
             uint8_t *scratch = lstage + kDecLitStage;

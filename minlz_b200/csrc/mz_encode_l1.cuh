@@ -385,20 +385,28 @@ __device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 
 
 // ---- tag filter in front of the slots ----------------------------------------
 // A random 32-byte slot read costs a whole 128-byte DRAM line, and only ~45 % of a
-// window's probes can verify at all (profiles/r02_tag_filter_sim.txt).  So every slot
-// has a 4-bit TAG of its 4 verify bytes in a second, dense table: 16 KiB per block,
-// 64 MiB for 4096 blocks in flight -- small enough to live in the 126 MB L2.  A probe
-// reads its tag first (an L2 hit); when the tag differs from the tag of the lane's own
-// 4 bytes the slot's bytes differ too, the probe CANNOT verify, and the DRAM line is
-// never fetched.  A matching tag (the real matches + 1/16 of the rest) fetches the
-// slot and verifies on the bytes as before, so every decision is unchanged.
-// Invariant: tag[h] == tag_of(verify bytes of slot h), kept by updating the nibble with
-// one atomic XOR (old ^ new) whenever the slot is overwritten; untouched slots hold
-// position 0, so the table starts as tag_of(src[0..4)) everywhere.
+// window's probes can verify at all (profiles/r02_tag_filter.txt).  So every slot has a
+// small TAG derived from its 4 verify bytes in a second, dense table.  A probe reads its
+// tag first; when it differs from the tag of the lane's own 4 bytes the slot's bytes
+// differ too, the probe CANNOT verify, and the DRAM line is never fetched.  A matching
+// tag (every real match + 2^-bits of the rest) fetches the slot and verifies on the
+// bytes as before, so every decision is unchanged.
+// Invariant: tag[h] == tag_of(verify bytes of slot h), kept by one atomic XOR
+// (old ^ new) whenever the slot is overwritten; untouched slots hold position 0, so
+// the table starts as tag_of(src[0..4)) everywhere.
+// Where the tags live decides what the filter is worth (B200, 4096 x 1 MiB, amd64 flavour):
+//   no filter                              111.7 ms   420 GB read
+//   4-bit tags in global memory (64 MiB)   132.2 ms   390 GB read  -- the tags do NOT stay in the
+//       126 MB L2 against 450 GB of streaming slot lines, with or without evict_last hints or a
+//       persisting set-aside: every tag read becomes one more DRAM line and one more dependent trip
+//   2-bit tags in global memory (32 MiB)   123.9 ms   295 GB read
+//   1-bit tags in SHARED memory (4 KiB per block, 28 blocks per SM)
+//                                          107.0 ms   274 GB read  <- the default: no extra traffic,
+//       no dependent L2 round trip; 2 bits per slot would need 224 KB per SM and do not fit.
 // MZ_ENC_TAGS: 0 = no filter, 1 = tags in global memory / L2 (MZ_ENC_TAG_BITS wide), 2 = 1-bit tags in
 // shared memory (4 KiB per block: no extra memory traffic and no dependent L2 round trip, half the power)
 #ifndef MZ_ENC_TAGS
-#define MZ_ENC_TAGS 1
+#define MZ_ENC_TAGS 2
 #endif
 #ifndef MZ_ENC_TAG_BITS
 #define MZ_ENC_TAG_BITS 4
@@ -408,7 +416,7 @@ __device__ __forceinline__ void slot_store(Slot *p, const uint4 &a, const uint4 
 #define MZ_ENC_TAG_BITS 1
 #endif
 #ifndef MZ_ENC_L2_HINTS
-#define MZ_ENC_L2_HINTS 1  // tags: L2 evict_last; slots: L2 evict_first (streamed once, 4.3 GB of them)
+#define MZ_ENC_L2_HINTS 0  // tags: L2 evict_last; slots: L2 evict_first.  Measured: no help for the tags, -5 % for the slots
 #endif
 constexpr int kTagBits = MZ_ENC_TAG_BITS;
 constexpr int kTagsPerWord = 32 / kTagBits;
