@@ -49,7 +49,7 @@
 
 namespace mz {
 
-constexpr int kDecSlots = 32;      // block slots per CTA (one parser lane each)
+constexpr int kDecSlots = 28;      // block slots per CTA (one parser lane and one copier warp each)
 constexpr int kDecCopiers = 28;    // copier warps per CTA
 constexpr int kDecLexers = 3;      // lexer warps per CTA (stream prefetch + token lengths for the parser)
 constexpr int kDecWarps = 1 + kDecCopiers + kDecLexers;
@@ -59,9 +59,10 @@ constexpr int kDecShort = 40;      // max literal / match length of a "short" to
 constexpr int kDecStage = kDecTok * 2 * kDecShort + 32;       // output image of a batch (+ alignment slack)
 constexpr int kDecLitStage = kDecTok * (8 + kDecShort) + 48;  // stream span of a batch
 constexpr int kDecScratch = 32 * 48 + 16;                     // per-lane 48-byte gather landing zone
-constexpr int kDescStride = 3 * kDecTok + 1;                  // words per (slot, buffer); odd -> conflict free
-constexpr int kDecRing = 512;                                 // per-slot ring of compressed bytes (+ as many token lengths)
-constexpr int kDecRingAhead = 496;                            // bytes kept requested ahead of the cursor
+constexpr int kDescStride = kDecTok + 2;                      // uint16 per (slot, buffer); 17 words -> conflict free
+constexpr int kDecRing = 1024;                                // per-slot ring of compressed bytes (+ as many token lengths)
+constexpr int kDecRingAhead = kDecRing - 32;                  // bytes kept requested ahead of the batch being copied
+constexpr uint32_t kDescGlobal = 0x8000;                      // descriptor flag: the token's header is not in the ring
 
 constexpr uint32_t kBatchLong = 0x100;   // the batch is a single long token
 constexpr uint32_t kBatchEnded = 0x200;  // the stream ended behind this batch (decode.go:615 check is due)
@@ -86,7 +87,7 @@ struct DecSlotState {
     int lx_lexed[2][kDecSlots];      // adv[] entries below this are valid
 };
 
-constexpr size_t kDecSmemBytes = sizeof(uint32_t) * 2 * kDecSlots * kDescStride + sizeof(DecSlotState) +
+constexpr size_t kDecSmemBytes = sizeof(uint16_t) * 2 * kDecSlots * kDescStride + 16 + sizeof(DecSlotState) +
                                  (size_t)kDecCopiers * (kDecStage + kDecLitStage + kDecScratch) +
                                  (size_t)kDecSlots * kDecRing * 2 + 64;
 
@@ -233,8 +234,9 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                  const uint64_t *__restrict__ dend, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t *desc = reinterpret_cast<uint32_t *>(smem_raw);  // [2][kDecSlots][kDescStride]: pos, header lo, header hi
-    DecSlotState *st = reinterpret_cast<DecSlotState *>(desc + 2 * kDecSlots * kDescStride);
+    // [2][kDecSlots][kDescStride]: offset of every token of the batch from the batch's first byte (| kDescGlobal)
+    uint16_t *desc = reinterpret_cast<uint16_t *>(smem_raw);
+    DecSlotState *st = reinterpret_cast<DecSlotState *>(smem_raw + ((sizeof(uint16_t) * 2 * kDecSlots * kDescStride + 15) & ~size_t(15)));
     uint8_t *copier_mem = reinterpret_cast<uint8_t *>(st + 1);
     copier_mem += (16 - (reinterpret_cast<uintptr_t>(copier_mem) & 15)) & 15;
     __shared__ int produced[2];  // produced[r & 1]: the parser emitted something in round r
@@ -277,6 +279,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
     if (threadIdx.x < kDecSlots) {
         st->count[0][threadIdx.x] = st->count[1][threadIdx.x] = 0;
         st->s_end[0][threadIdx.x] = st->s_end[1][threadIdx.x] = 0;
+        st->s_first[0][threadIdx.x] = st->s_first[1][threadIdx.x] = 0;
         st->d[threadIdx.x] = 0;
         st->off[threadIdx.x] = 1;  // decode.go:186
         st->dead[threadIdx.x] = 0;
@@ -288,113 +291,140 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
         const int rb = wb ^ 1;     // buffer the copiers drain (filled in the previous round)
         if (warp == 0) {
             // ================= PARSER =================
-            uint32_t *my = desc + (wb * kDecSlots + lane) * kDescStride;
+            uint16_t *my = desc + (wb * kDecSlots + min(lane, kDecSlots - 1)) * kDescStride;
             // what the lexers published at the end of the previous round
             const int p_ready = lane < nslots ? st->lx_ready[rb][lane] : 0;
             const int p_lexed = lane < nslots ? st->lx_lexed[rb][lane] : 0;
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(p_ring);
-            auto ring_ok_at = [&](int ap) { return ap + 8 <= p_ready || p_aend <= p_ready; };
-            auto ring_load = [&](int ap) {
-                const uint32_t a4 = (uint32_t)ap >> 2;
-                const uint32_t w0 = rw[a4 & (kDecRing / 4 - 1)], w1 = rw[(a4 + 1) & (kDecRing / 4 - 1)],
-                               w2 = rw[(a4 + 2) & (kDecRing / 4 - 1)];
-                const unsigned sh = ((unsigned)ap & 3u) * 8;
-                return (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
-            };
             int cnt = 0;
             uint32_t flags = 0;
-            bool cut = false;
-            const uint32_t s_first = (uint32_t)p_s;
+            const int s_first = p_s;
             // end of stream is noticed at the start of a round (decode.go:615 is checked
             // by the copier that owns the output cursor)
             if (!p_done && p_s >= p_slen) {
                 p_done = true;
                 flags = kBatchEnded;
             }
-            // One token per lane per step.  No votes and no warp-level early exits in here:
-            // every instruction on this path is paid by every block of the CTA on every
-            // token.  The chain is  a -> adv[a] -> a + adv;  rare cases (bytes not lexed
-            // yet, extended lengths) are plain divergent branches.
-#pragma unroll 2
+            bool stop = p_done;  // no more tokens from this lane in this round
+            // One token per lane per step, and as little as possible per step: every instruction
+            // here is on the serial chain of 28 blocks.  The chain is  a -> adv[a] -> a + adv.
+            // Tokens the lexers left alone (extended lengths), bytes not lexed yet and tokens
+            // that overrun the stream take the cold path.
+#pragma unroll 4
             for (int k = 0; k < kDecTok; k++) {
-                const bool live = !p_done && !cut && p_s < p_slen;
+                const bool live = !stop && p_s < p_slen;
                 const int a = p_lead + p_s;
                 int adv = 0;
                 if (live && a < p_lexed) adv = p_adv[a & (kDecRing - 1)];
-                uint64_t w8 = ring_load(a);  // the descriptor's header bytes (valid below p_lexed)
-                bool lng = false;
-                if (live && adv == 0) {  // not lexed yet, or a token the lexers leave to this path
-                    if (!ring_ok_at(a)) w8 = ldg_window(p_sp, p_s, p_slen);  // first rounds / after a long literal run
-                    const uint32_t lo = (uint32_t)w8;
-                    const uint32_t e = st->lut[lo & 0xff];
-                    adv = (int)(e & 0x7f);
-                    if ((e & 0x80) != 0 || ((lo & 7) == 7 && ((lo >> 5) & 63) > 60)) {  // extended length
-                        const PTok t = parse_token_bf(w8);
-                        adv = (int)(t.hdr + t.lit);
-                        lng = t.lit > kDecShort || t.mlen > kDecShort;
+                if (live) {
+                    if (adv != 0 && adv <= p_slen - p_s) {
+                        my[cnt] = (uint16_t)(p_s - s_first);
+                        p_s += adv;
+                        cnt++;
+                    } else {
+                        // ---- cold path ----
+                        uint32_t where = 0;
+                        uint64_t w8;
+                        if (a + 8 <= p_ready || p_aend <= p_ready) {
+                            const uint32_t *rw = reinterpret_cast<const uint32_t *>(p_ring);
+                            const uint32_t a4 = (uint32_t)a >> 2;
+                            const uint32_t w0 = rw[a4 & (kDecRing / 4 - 1)], w1 = rw[(a4 + 1) & (kDecRing / 4 - 1)],
+                                           w2 = rw[(a4 + 2) & (kDecRing / 4 - 1)];
+                            const unsigned sh = ((unsigned)a & 3u) * 8;
+                            w8 = (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
+                        } else {  // first rounds / after a long literal run: not in the ring (yet)
+                            w8 = ldg_window(p_sp, p_s, p_slen);
+                            where = kDescGlobal;
+                        }
+                        const uint32_t lo = (uint32_t)w8;
+                        const uint32_t e = st->lut[lo & 0xff];
+                        adv = (int)(e & 0x7f);
+                        bool lng = false;
+                        if ((e & 0x80) != 0 || ((lo & 7) == 7 && ((lo >> 5) & 63) > 60)) {  // extended length
+                            const PTok t = parse_token_bf(w8);
+                            adv = (int)(t.hdr + t.lit);
+                            lng = t.lit > kDecShort || t.mlen > kDecShort;
+                        }
+                        // header and literals must lie inside the stream (decode.go:221,410 src side)
+                        if (adv > p_slen - p_s) {
+                            flags |= kBatchBad;
+                            p_done = true;
+                            stop = true;
+                        } else if (lng && cnt > 0) {
+                            stop = true;  // a long token travels alone: it starts the next batch
+                        } else if ((uint32_t)(p_s - s_first) >= kDescGlobal) {
+                            stop = true;  // the 15-bit offset is used up: next batch (cannot happen with 32 short tokens)
+                        } else {
+                            my[cnt] = (uint16_t)((uint32_t)(p_s - s_first) | where);
+                            p_s += adv;
+                            cnt++;
+                            if (lng) {
+                                flags |= kBatchLong;
+                                stop = true;
+                            }
+                        }
                     }
                 }
-                // header and literals must lie inside the stream (decode.go:221,410 src side)
-                const bool bad = adv > p_slen - p_s;
-                const bool defer = lng && cnt > 0;  // a long token travels alone: it starts the next batch
-                const bool emit = live && !bad && !defer;
-                if (emit) {
-                    my[0 * kDecTok + cnt] = (uint32_t)p_s;
-                    my[1 * kDecTok + cnt] = (uint32_t)w8;
-                    my[2 * kDecTok + cnt] = (uint32_t)(w8 >> 32);
-                }
-                if (live && bad) {
-                    flags |= kBatchBad;
-                    p_done = true;
-                }
-                if (emit && lng) flags |= kBatchLong;
-                cut = cut || (live && !bad && lng);
-                p_s = emit ? p_s + adv : p_s;
-                cnt += emit ? 1 : 0;
             }
-            st->count[wb][lane] = (uint32_t)cnt | flags;
-            st->s_first[wb][lane] = s_first;
-            st->s_end[wb][lane] = (uint32_t)p_s;
+            if (lane < kDecSlots) {
+                st->count[wb][lane] = (uint32_t)cnt | flags;
+                st->s_first[wb][lane] = (uint32_t)s_first;
+                st->s_end[wb][lane] = (uint32_t)p_s;
+            }
             // a round that emits nothing (no tokens, no end / error notices) means
             // every block of this CTA is finished
             const bool some = __any_sync(kFullMask, cnt > 0 || flags != 0);
             if (lane == 0) produced[wb] = some ? 1 : 0;
         } else if (warp > kDecCopiers) {
             // ================= LEXERS =================
-            cp_async_wait_all();  // what this warp requested in earlier rounds has landed
-            __syncwarp();
+            // pass 1: request the next stretch of every slot of mine.  The ring keeps the batch the
+            // copiers work on in this round (they read the token headers from it) and runs ahead of it.
             for (int slot = warp - 1 - kDecCopiers; slot < nslots; slot += kDecLexers) {
                 const int lead = st->lx_lead[slot], aend = st->lx_aend[slot];
-                int afill = st->lx_fill[slot], done = st->lx_done[slot];
+                int afill = st->lx_fill[slot];
+                const int keep = lead + (int)st->s_first[rb][slot];  // first byte of the batch being copied
+                const int cur = lead + (int)st->s_end[rb][slot];     // the parser's cursor
+                if (afill < (cur & ~15)) afill = cur & ~15;          // a long literal run skipped ahead of everything requested
+                const int want = min((aend + 15) & ~15, (keep + kDecRingAhead) & ~15);
                 uint8_t *ring = rings + (size_t)slot * kDecRing;
-                uint8_t *adv = advs + (size_t)slot * kDecRing;
-                const int ready = afill;  // everything requested so far has landed (wait_all above)
-                // the parser's cursor as of the end of the previous round: bytes before it are dead
-                // (their ring cells get reused), so neither lex nor keep them
+                const uintptr_t abase = (uintptr_t)st->lx_abase[slot];
+                for (int chunk = afill + 16 * lane; chunk < want; chunk += 16 * 32)
+                    cp_async16(ring + (chunk & (kDecRing - 1)), reinterpret_cast<const void *>(abase + (uintptr_t)chunk));
+                if (want > afill) afill = want;
+                if (lane == 0) st->lx_fill[slot] = afill;
+            }
+            cp_async_wait_all();  // rounds are long (the copiers): wait for the bytes and lex them right away
+            __syncwarp();
+            // pass 2: token lengths.  adv[i] = header + literal bytes of a token that starts at byte i,
+            // 0 when the length is extended (parser's cold path).  An entry needs bytes i, i+1; four
+            // offsets per lane per step from two aligned words.
+            for (int slot = warp - 1 - kDecCopiers; slot < nslots; slot += kDecLexers) {
+                const int lead = st->lx_lead[slot], aend = st->lx_aend[slot];
+                const int afill = st->lx_fill[slot];
+                int done = st->lx_done[slot];
                 const int cur = lead + (int)st->s_end[rb][slot];
-                if (done < (cur & ~15)) done = cur & ~15;
-                // 1. token lengths of the bytes that have landed.  An entry needs bytes i, i+1; the
-                //    parser also takes the 8 descriptor bytes of a lexed token from the ring, so the
-                //    frontier stays 8 bytes behind what has landed (or reaches the stream's end).
+                if (done < (cur & ~15)) done = cur & ~15;  // bytes behind the cursor are dead
+                const uint32_t *ring = reinterpret_cast<const uint32_t *>(rings + (size_t)slot * kDecRing);
+                uint32_t *adv = reinterpret_cast<uint32_t *>(advs + (size_t)slot * kDecRing);
+                // the frontier stays 8 bytes behind what has landed (the copiers take 8 header bytes of a
+                // lexed token from the ring), or reaches the end of the stream
                 const int lim = afill >= aend ? aend : afill - 8;
-                for (int i = done + lane; i < lim; i += 32) {
-                    const uint32_t b0 = ring[i & (kDecRing - 1)], b1 = ring[(i + 1) & (kDecRing - 1)];
-                    uint32_t e = st->lut[b0];
-                    if ((e & 0x80) != 0 || ((b0 & 7) == 7 && (((b0 | b1 << 8) >> 5) & 63) > 60)) e = 0;  // extended: parser's path
-                    adv[i & (kDecRing - 1)] = (uint8_t)e;
+                for (int i = (done & ~3) + 4 * lane; i < lim; i += 4 * 32) {
+                    const uint32_t w0 = ring[(i >> 2) & (kDecRing / 4 - 1)], w1 = ring[((i >> 2) + 1) & (kDecRing / 4 - 1)];
+                    uint32_t out = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t b01 = __funnelshift_r(w0, w1, 8 * j) & 0xffffu;  // bytes i+j, i+j+1
+                        uint32_t e = st->lut[b01 & 0xff];
+                        if ((e & 0x80) != 0 || ((b01 & 7) == 7 && ((b01 >> 5) & 63) > 60)) e = 0;
+                        out |= e << (8 * j);
+                    }
+                    adv[(i >> 2) & (kDecRing / 4 - 1)] = out;
                 }
                 if (lim > done) done = lim;
-                // 2. request the next stretch ahead of the cursor
-                if (afill < (cur & ~15)) afill = cur & ~15;  // a long literal run skipped ahead of everything requested
-                const int want = min((aend + 15) & ~15, (cur + kDecRingAhead) & ~15);
-                const int chunk = afill + 16 * lane;
-                if (chunk < want) cp_async16(ring + (chunk & (kDecRing - 1)), reinterpret_cast<const void *>((uintptr_t)st->lx_abase[slot] + (uintptr_t)chunk));
-                if (want > afill) afill = min(want, afill + 16 * 32);
                 __syncwarp();
                 if (lane == 0) {
-                    st->lx_fill[slot] = afill;
                     st->lx_done[slot] = done;
-                    st->lx_ready[wb][slot] = ready;
+                    st->lx_ready[wb][slot] = afill;
                     st->lx_lexed[wb][slot] = done;
                 }
             }
@@ -419,12 +449,26 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 const uint32_t d_base = st->d[slot];
                 const uint32_t off_carry = st->off[slot];
                 // ---- decode my token ----
-                const uint32_t *dsc = desc + (rb * kDecSlots + slot) * kDescStride;
+                const uint16_t *dsc = desc + (rb * kDecSlots + slot) * kDescStride;
+                const uint32_t slen = (uint32_t)(send[b] - sbeg[b]);
                 uint32_t tp = 0, lit = 0, mlen = 0, off_tok = 0, hdr = 0;
                 bool isrep = false;
                 if (lane < n) {
-                    tp = dsc[lane];
-                    const PTok t = parse_token_bf((uint64_t)dsc[2 * kDecTok + lane] << 32 | dsc[kDecTok + lane]);
+                    const uint32_t dw = dsc[lane];
+                    tp = st->s_first[rb][slot] + (dw & (kDescGlobal - 1));
+                    uint64_t w8;
+                    if (dw & kDescGlobal) {  // parsed before its bytes were in the ring
+                        w8 = ldg_window(sp, tp, slen);
+                    } else {  // the 8 header bytes from the slot's ring (kept by the lexers while this batch is copied)
+                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(rings + (size_t)slot * kDecRing);
+                        const uint32_t ap = (uint32_t)st->lx_lead[slot] + tp;
+                        const uint32_t a4 = ap >> 2;
+                        const uint32_t w0 = rw[a4 & (kDecRing / 4 - 1)], w1 = rw[(a4 + 1) & (kDecRing / 4 - 1)],
+                                       w2 = rw[(a4 + 2) & (kDecRing / 4 - 1)];
+                        const unsigned sh = (ap & 3u) * 8;
+                        w8 = (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
+                    }
+                    const PTok t = parse_token_bf(w8);
                     lit = t.lit;
                     mlen = t.mlen;
                     off_tok = t.off;
