@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -52,6 +53,28 @@ bool validate_on() {
 thread_local char g_err[512] = "";
 thread_local float g_last_kernel_ms = 0.f;
 
+// Launch gate of the asynchronous calls (mzcu_submit_*): the FIRST kernel launch of every submitted
+// job happens in submission order, so "decode of batch k, then encode of batch k+1" reaches the
+// device in that order whatever the job threads' start-up timing (see DeviceState::dec_done).
+std::mutex g_gate_mu;
+std::condition_variable g_gate_cv;
+int64_t g_gate_next = 1;             // ticket whose turn it is
+thread_local int64_t t_ticket = 0;   // this thread's job ticket; 0 = not a submitted job, or already through
+void gate_enter() {
+    if (!t_ticket) return;
+    std::unique_lock<std::mutex> lk(g_gate_mu);
+    g_gate_cv.wait(lk, [] { return g_gate_next == t_ticket; });
+}
+void gate_leave() {
+    if (!t_ticket) return;
+    {
+        std::lock_guard<std::mutex> lk(g_gate_mu);
+        g_gate_next = t_ticket + 1;
+    }
+    t_ticket = 0;
+    g_gate_cv.notify_all();
+}
+
 int fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -90,6 +113,13 @@ struct DeviceState {
     std::atomic<unsigned> next_counter{0};
     std::mutex ws_mu;
     std::vector<TableWs> table_ws;
+    // Launch order across concurrent host calls: an encode launch is a persistent kernel that holds
+    // every SM for ~100 ms, a decode launch is short but its download is long.  A decode kernel that
+    // queues behind an encode kernel delays that download by the whole encode; so an encode launch
+    // waits for the decode kernels already submitted on this device (<= one decode's duration) and
+    // the download then overlaps the encode.
+    cudaEvent_t dec_done = nullptr;
+    std::mutex order_mu;
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -141,6 +171,7 @@ int init_device(int device) {
             if (g && atoi(g) > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(g) << 20) != cudaSuccess)
                 cudaGetLastError();
         }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st.dec_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&st.counters, kCounterSlots * sizeof(int));
         if (e == cudaSuccess) e = cudaMalloc(&st.crc_tabs, sizeof(mz::CrcTables));
         if (e == cudaSuccess) {
@@ -182,9 +213,16 @@ int launch_decode(int device, int nblk, const uint8_t *src, const uint64_t *sbeg
     if (slots > mz::kDecSlots) slots = mz::kDecSlots;
     if (slots < 1) slots = 1;
     const int grid = (nblk + slots - 1) / slots;
+    gate_enter();
     mz::decode_pc_kernel<<<grid, mz::kDecThreads, mz::kDecSmemBytes, stream>>>(nblk, slots, src, sbeg, send, dst, dbeg,
                                                                                dend, status);
-    CU_TRY(cudaGetLastError());
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_dev[device].order_mu);
+        le = cudaEventRecord(g_dev[device].dec_done, stream);
+    }
+    gate_leave();
+    if (le != cudaSuccess) return fail(MZCU_ERR_CUDA, "decode launch: %s", cudaGetErrorString(le));
     return MZCU_OK;
 }
 
@@ -221,6 +259,18 @@ int launch_encode(int device, int level, int nblk, const uint8_t *src, const uin
     DeviceState &st = g_dev[device];
     int *counter = st.counters + (st.next_counter.fetch_add(1) % kCounterSlots);
     CU_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    gate_enter();
+    {
+        std::lock_guard<std::mutex> lk(st.order_mu);
+        cudaError_t we = cudaStreamWaitEvent(stream, st.dec_done, 0);  // short decode kernels first (see DeviceState)
+        if (we != cudaSuccess) {
+            gate_leave();
+            return fail(MZCU_ERR_CUDA, "encode launch order: %s", cudaGetErrorString(we));
+        }
+    }
+    struct GateGuard {
+        ~GateGuard() { gate_leave(); }
+    } gate_guard;  // released after the launch below (or on any early return)
     if (level == MZCU_LEVEL_FASTEST || level == MZCU_LEVEL_SUPERFAST) {
         // one block per warp, all resident: grid = min(blocks, what fits on the chip)
         int grid = (nblk + mz::kEncL1Warps - 1) / mz::kEncL1Warps;
@@ -927,13 +977,16 @@ int64_t submit_job(F &&call) {
     Job *j = new Job();
     int bound = -1;
     cudaGetDevice(&bound);
-    j->th = std::thread([j, call, bound] {
-        if (bound >= 0) cudaSetDevice(bound);
-        j->rc = call();
-        if (j->rc) snprintf(j->err, sizeof j->err, "%s", g_err);
-    });
     std::lock_guard<std::mutex> lk(g_job_mu);
     const int64_t id = g_next_job++;
+    j->th = std::thread([j, call, bound, id] {
+        if (bound >= 0) cudaSetDevice(bound);
+        t_ticket = id;
+        j->rc = call();
+        if (j->rc) snprintf(j->err, sizeof j->err, "%s", g_err);
+        gate_enter();  // a job that never launched still takes (and passes on) its turn
+        gate_leave();
+    });
     g_jobs[id] = j;
     return id;
 }

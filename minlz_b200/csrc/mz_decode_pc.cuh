@@ -97,6 +97,30 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---- bulk copies (the TMA engine's 1-D form, SASS UBLKCP) with mbarrier completion -------------
+// One thread hands the copy engine a contiguous, 16-byte aligned stretch of global memory; the bytes
+// land in shared memory without passing through registers and signal an mbarrier by byte count.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @!p bra W;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 // Warp-cooperative forward copy dst[0..n) = src[0..n) with memmove-forward
 // semantics for overlapping ranges (dst - src = off > 0), as decode.go:339-358.
 __device__ __forceinline__ void warp_copy_overlap(uint8_t *dstp, uint32_t off, uint32_t n, int lane) {
@@ -240,6 +264,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
     uint8_t *copier_mem = reinterpret_cast<uint8_t *>(st + 1);
     copier_mem += (16 - (reinterpret_cast<uintptr_t>(copier_mem) & 15)) & 15;
     __shared__ int produced[2];  // produced[r & 1]: the parser emitted something in round r
+    __shared__ __align__(8) uint64_t lexer_bar[kDecLexers];  // bulk-copy completion, one phase per round
 
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
@@ -275,6 +300,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
         st->lx_ready[0][lane] = st->lx_ready[1][lane] = 0;
         st->lx_lexed[0][lane] = st->lx_lexed[1][lane] = 0;
     }
+    if (threadIdx.x < kDecLexers) mbar_init(&lexer_bar[threadIdx.x], 1);
     if (threadIdx.x < 256) st->lut[threadIdx.x] = dec_lut_entry(threadIdx.x);
     if (threadIdx.x < kDecSlots) {
         st->count[0][threadIdx.x] = st->count[1][threadIdx.x] = 0;
@@ -378,6 +404,8 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             // ================= LEXERS =================
             // pass 1: request the next stretch of every slot of mine.  The ring keeps the batch the
             // copiers work on in this round (they read the token headers from it) and runs ahead of it.
+            uint64_t *lx_bar = &lexer_bar[warp - 1 - kDecCopiers];
+            unsigned lx_tx = 0;
             for (int slot = warp - 1 - kDecCopiers; slot < nslots; slot += kDecLexers) {
                 const int lead = st->lx_lead[slot], aend = st->lx_aend[slot];
                 int afill = st->lx_fill[slot];
@@ -387,13 +415,23 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 const int want = min((aend + 15) & ~15, (keep + kDecRingAhead) & ~15);
                 uint8_t *ring = rings + (size_t)slot * kDecRing;
                 const uintptr_t abase = (uintptr_t)st->lx_abase[slot];
-                for (int chunk = afill + 16 * lane; chunk < want; chunk += 16 * 32)
-                    cp_async16(ring + (chunk & (kDecRing - 1)), reinterpret_cast<const void *>(abase + (uintptr_t)chunk));
+                // [afill, want) is contiguous in memory and 16-byte aligned at both ends: one bulk copy,
+                // two when it wraps around the ring
+                if (lane == 0 && want > afill) {
+                    const unsigned o = (unsigned)afill & (kDecRing - 1);
+                    const unsigned len = (unsigned)(want - afill);
+                    const unsigned first = min(len, (unsigned)kDecRing - o);
+                    bulk_copy_g2s(ring + o, reinterpret_cast<const void *>(abase + (uintptr_t)afill), first, lx_bar);
+                    if (len > first)
+                        bulk_copy_g2s(ring, reinterpret_cast<const void *>(abase + (uintptr_t)afill + first), len - first, lx_bar);
+                    lx_tx += len;
+                }
                 if (want > afill) afill = want;
                 if (lane == 0) st->lx_fill[slot] = afill;
             }
-            cp_async_wait_all();  // rounds are long (the copiers): wait for the bytes and lex them right away
-            __syncwarp();
+            // rounds are long (the copiers): wait for the bytes and lex them right away
+            if (lane == 0) mbar_arrive_expect_tx(lx_bar, lx_tx);
+            mbar_wait(lx_bar, (unsigned)round & 1u);
             // pass 2: token lengths.  adv[i] = header + literal bytes of a token that starts at byte i,
             // 0 when the length is extended (parser's cold path).  An entry needs bytes i, i+1; four
             // offsets per lane per step from two aligned words.

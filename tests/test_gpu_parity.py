@@ -416,3 +416,36 @@ def test_random_structures_fuzz_batch(oracle):
         for i, data in enumerate(blocks):
             got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
             assert got == oracle.encode_block(data, level), (level, i, len(data))
+
+
+@pytest.mark.parametrize("level", [1, 2, -1])
+def test_go_flavour_8mib_class(oracle, level):
+    """The library's default flavour (pure-Go functions) at the 8 MiB block size of BASELINE
+    config 5, with real data: text, binary structs, a far copy beyond the copy3 range (the
+    minSrcPos guards of encode_l1.go:83,147 / encode_l2.go:118 decide), a 3 MiB period and a
+    large-offset pattern.  Encoder bytes == oracle restatement, and they decode to the input."""
+    import synth
+    assert mz.get_encoder_flavor() == mz.FlavorGo
+    items = [(k, synth.make_blocks(k, 1, 8 << 20).numpy()[0].tobytes()) for k in ("text", "binary")]
+    items.append(("large_offset", patterns.large_offset(8 << 20, (2 << 20) + 70000)))
+    rng = np.random.default_rng(7)
+    per = rng.integers(0, 256, 3 << 20, dtype=np.uint8)
+    items.append(("period3MiB", np.concatenate([per, per, per[: 2 << 20]]).tobytes()))
+    text = synth.make_blocks("text", 1, 8 << 20).numpy()[0].copy()
+    text[5 << 20:] = text[: 3 << 20]
+    items.append(("text-far-copy", text.tobytes()))
+    raws = [d for _, d in items]
+    src, soff = _cat(raws)
+    dst, doff, out_len = mz.encode_blocks(src, soff, level)
+    streams = []
+    for i, (name, data) in enumerate(items):
+        want = oracle.encode_block(data, level)
+        got = dst[int(doff[i]):int(doff[i]) + int(out_len[i])].tobytes()
+        assert got == want, (name, level, len(got), len(want))
+        streams.append(got)
+    live = [i for i in range(len(items)) if streams[i]]
+    csrc, csoff = _cat([streams[i] for i in live])
+    _, cdoff = _cat([raws[i] for i in live])
+    out, status = mz.decode_blocks(csrc, csoff, cdoff)
+    assert not status.any()
+    assert out.tobytes() == b"".join(raws[i] for i in live)
