@@ -22,6 +22,9 @@ import (
 	"unsafe"
 )
 
+// cudaEnabled gates the batch-point branches in writer.go / reader.go (a `const false` twin lives in a !cuda file).
+const cudaEnabled = true
+
 var errCuda = errors.New("minlz: cuda backend failure")
 
 // call runs one C entry point and, on failure, fetches its message.  The message is

@@ -167,7 +167,13 @@ def Decode(dst, src):
     """decode.go:50-78 (MinLZ blocks; the Snappy/S2 fallback for blocks whose
     first byte is not 0 stays in host Go and raises ErrUnsupported here)."""
     s = _np(src)
-    dlen = DecodedLen(s)
+    ok, dlen = IsMinLZ(s)
+    # nothing is allocated before the block is known to be MinLZ of a legal size (decode.go:59-68:
+    # a first byte != 0 is a Snappy varint of up to 4 GiB; s2 rejects it above its MaxBlockSize)
+    if not ok:
+        raise ErrUnsupported()
+    if dlen > MaxBlockSize:
+        raise ErrTooLarge()
     out = np.zeros(max(dlen, 1), dtype=np.uint8)
     r = _lib.load().mzcu_decode(out.ctypes.data, dlen, _ptr(s), s.size)
     if r == _E_CORRUPT:
@@ -222,7 +228,12 @@ def DecodeBatch(blocks, device=-1):
     pre = {}
     for i, a in enumerate(arrs):
         try:
-            sizes.append(DecodedLen(a))
+            ok, n = IsMinLZ(a)
+            if not ok:
+                raise ErrUnsupported()
+            if n > MaxBlockSize:
+                raise ErrTooLarge()
+            sizes.append(n)
         except MinLZError as e:
             pre[i] = e
             sizes.append(0)

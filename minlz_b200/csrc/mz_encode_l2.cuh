@@ -14,16 +14,12 @@
 // long at s+1) in one round trip; match extension is lane parallel.
 //
 // Table entries are SNAPSHOTS, as in the L1 kernel: a long-table entry is
-// {position : 24 | the byte BEFORE it : 8, the 12 source bytes at it} (16 B), a
-// short-table entry {position : 24 | byte before : 8, 4 bytes} (8 B).  The
-// reference's table -> src[candidate] chain (two dependent DRAM round trips per
-// step) becomes one, and for a long-table candidate so do the two that follow a
-// hit: the backward extension almost always stops at once (95 %: decided by the
-// byte before the candidate) and two thirds of the matches end within 12 bytes of
-// the probe (profiles/r02_l2_walk_sim.txt), so neither has to touch src[candidate].
-// The bytes are copies of immutable source bytes, so every decision is unchanged.
-// An untouched (zero) entry stands for candidate 0, whose bytes are src[0..12)
-// (encode_l2.go:84,121-130).  2.1 MiB of workspace per in-flight block.
+// {position, the 8 source bytes at it} (16 B), a short-table entry {position, 4
+// bytes} (8 B).  The reference's table -> src[candidate] chain (two dependent DRAM
+// round trips per step) becomes one; the bytes are copies of immutable source
+// bytes, so every decision is unchanged.  An untouched (zero) entry stands for
+// candidate 0, whose bytes are src[0..8) (encode_l2.go:84,121-130).  2.1 MiB of
+// workspace per in-flight block.
 #pragma once
 
 #include "mz_common.cuh"
@@ -42,57 +38,12 @@ struct L2Params {
 constexpr int kEncL2Warps = 4;
 constexpr size_t kEncL2WsBytesPerWarp = ((size_t)(1 << 17) * 16) + ((size_t)(1 << 14) * 8);  // 2 MiB + 128 KiB
 
-// Source bytes around a position as the snapshot entries hold them: the byte before it and the
-// 16 bytes from it (zero filled past n; never touches a word that holds no byte < n).
-struct L2Bytes {
-    uint32_t back;       // src[pos-1] (0 at pos == 0)
-    uint32_t f[4];       // src[pos .. pos+16)
-    __device__ __forceinline__ uint64_t lo8() const { return (uint64_t)f[1] << 32 | f[0]; }
-};
-__device__ __forceinline__ L2Bytes l2_bytes_at(const uint8_t *src, int pos, int n) {
-    L2Bytes r;
-    if (pos >= 1 && pos + 16 <= n) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(src + pos - 1);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
-        const unsigned sh = (unsigned)(a & 3) * 8;
-        // 17 bytes from a = five aligned words; the fifth always holds src[pos+15] < n
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh),
-                       b3 = __funnelshift_r(w3, w4, sh), b4 = w4 >> sh;
-        r.back = b0 & 0xffu;
-        r.f[0] = __funnelshift_r(b0, b1, 8);
-        r.f[1] = __funnelshift_r(b1, b2, 8);
-        r.f[2] = __funnelshift_r(b2, b3, 8);
-        r.f[3] = __funnelshift_r(b3, b4, 8);
-    } else {  // block edges
-        r.back = pos >= 1 ? src[pos - 1] : 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t v = 0;
-            for (int i = 0; i < 4; i++)
-                if (pos + 4 * j + i < n) v |= (uint32_t)src[pos + 4 * j + i] << (8 * i);
-            r.f[j] = v;
-        }
-    }
-    return r;
+// long-table entry {pos, 8 bytes at pos}; short-table entry {pos, 4 bytes at pos}
+__device__ __forceinline__ void l2_put_long(uint4 *t, uint32_t h, int pos, uint64_t bytes) {
+    t[h] = make_uint4((uint32_t)pos, (uint32_t)bytes, (uint32_t)(bytes >> 32), 0u);
 }
-// the same for position pos+1, from the bytes of pos
-__device__ __forceinline__ L2Bytes l2_bytes_next(const L2Bytes &b) {
-    L2Bytes r;
-    r.back = b.f[0] & 0xffu;
-    r.f[0] = __funnelshift_r(b.f[0], b.f[1], 8);
-    r.f[1] = __funnelshift_r(b.f[1], b.f[2], 8);
-    r.f[2] = __funnelshift_r(b.f[2], b.f[3], 8);
-    r.f[3] = b.f[3] >> 8;  // its last byte is unknown: entries only keep 12
-    return r;
-}
-
-// long-table entry {pos | byte before << 24, 12 bytes at pos}; short-table entry {pos | byte before << 24, 4 bytes}
-__device__ __forceinline__ void l2_put_long(uint4 *t, uint32_t h, int pos, const L2Bytes &b) {
-    t[h] = make_uint4((uint32_t)pos | b.back << 24, b.f[0], b.f[1], b.f[2]);
-}
-__device__ __forceinline__ void l2_put_short(uint2 *t, uint32_t h, int pos, const L2Bytes &b) {
-    t[h] = make_uint2((uint32_t)pos | b.back << 24, b.f[0]);
+__device__ __forceinline__ void l2_put_short(uint2 *t, uint32_t h, int pos, uint64_t bytes) {
+    t[h] = make_uint2((uint32_t)pos, (uint32_t)bytes);
 }
 
 // 8 bytes at pos, zero filled past n; never touches a word with no byte < n.
@@ -133,6 +84,65 @@ __device__ __forceinline__ int extend_to_end(const uint8_t *src, int n, int s, i
         int add = diff ? (__ffsll((long long)diff) - 1) >> 3 : 0;
         add = __shfl_sync(kFullMask, add, f);
         return s + 8 * f + add;
+    }
+}
+
+// ---- table inserts of a match, one per lane ------------------------------------
+// After every match the reference re-indexes its interior: the two ends in both tables and every
+// other position of the middle in the long table (encode_l2.go:183-195,303-326; gen.go:1921-1978)
+// -- 7.7 inserts per search step on the benchmark's blocks, and in a walk whose speed is the
+// latency of ONE warp's instruction chain that was half of all instructions.  Here lane r performs
+// the r-th insert of the reference's serial order (32 per pass): position, 8 source bytes, hash,
+// store.  Nothing reads the tables in between, so only the final state matters: when two inserts
+// of a pass hit the same slot of the same table the later one in serial order -- the higher lane --
+// is the one that stores ("later write wins"), found with one match.any on (table, slot).
+enum { kL2OrderGo = 0, kL2OrderAsm = 1, kL2OrderRepeat = 2 };
+template <int kOrder, class H>
+__device__ __forceinline__ void l2_index_match(const H &P, uint4 *lTable, uint2 *sTable, const uint8_t *src, const int base,
+                                               const int e, const int lane) {
+    int total;
+    int mid = 0;
+    if (kOrder == kL2OrderRepeat) {
+        // while (index0 < index1) { L[index0] S[index0+1] L[index1] S[index1+1]; index0 += 2; index1 -= 2 }
+        const int span = e - base - 3;  // index1 - index0 at the start
+        total = span > 0 ? 4 * ((span + 3) >> 2) : 0;
+    } else {
+        // L[base+1] S[base+2] L[e-2] S[e-1] (Asm: L L S S), then index0 = base+2, index1 = e-3,
+        // index2 = (index0 + index1 + 1) >> 1; while (index2 < index1) { L[index0] L[index2]; += 2 }
+        mid = (base + 2 + e - 3 + 1) >> 1;
+        const int left = e - 3 - mid;
+        total = 4 + (left > 0 ? 2 * ((left + 1) >> 1) : 0);
+    }
+    for (int r0 = 0; r0 < total; r0 += 32) {
+        const int r = r0 + lane;
+        const bool act = r < total;
+        int pos = 0;
+        bool is_short = false;
+        if (kOrder == kL2OrderRepeat) {
+            const int j = r >> 2, t = r & 3;
+            pos = (t & 2) ? e - 2 - 2 * j : base + 1 + 2 * j;
+            is_short = t & 1;
+            pos += is_short ? 1 : 0;
+        } else if (r < 4) {
+            const bool second = kOrder == kL2OrderAsm ? (r & 1) : (r & 2);  // which end
+            is_short = kOrder == kL2OrderAsm ? (r & 2) : (r & 1);
+            pos = (second ? e - 2 : base + 1) + (is_short ? 1 : 0);
+        } else {
+            const int k = (r - 4) >> 1;
+            pos = ((r & 1) ? mid : base + 2) + 2 * k;
+        }
+        uint64_t cv = 0;
+        uint32_t key = 0x20000000u + (uint32_t)lane;  // idle lanes: keys of their own
+        if (act) {
+            cv = ldg_u64_unaligned(src + pos);  // pos + 8 <= n: the caller indexes only behind e < sLimit
+            key = is_short ? (0x80000000u | P.hashS(cv)) : P.hashL(cv);
+        }
+        const unsigned grp = __match_any_sync(kFullMask, key);
+        if (act && (grp >> lane) == 1u) {  // no later insert of this pass on my slot
+            if (is_short) l2_put_short(sTable, key & 0x7fffffffu, pos, cv);
+            else l2_put_long(lTable, key, pos, cv);
+        }
+        __syncwarp();
     }
 }
 
@@ -188,181 +198,137 @@ struct L2Records {
     }
 };
 
-// ---- shared pieces of the two flavours' walks --------------------------------
-// Inserts of the match interior: all lanes load (one broadcast transaction), lane 0 stores, so the
-// stores of one walk keep their program order ("later write wins", as in the serial code).
-template <class H>
-__device__ __forceinline__ void l2_index_long(const H &P, uint4 *lTable, const uint8_t *src, int n, int pos, int lane) {
-    const L2Bytes b = l2_bytes_at(src, pos, n);
-    if (lane == 0) l2_put_long(lTable, P.hashL(b.lo8()), pos, b);
-}
-// long[pos] and short[pos+1] from one load (encode_l2.go:186-195,303-310)
-template <class H>
-__device__ __forceinline__ void l2_index_pair(const H &P, uint4 *lTable, uint2 *sTable, const uint8_t *src, int n, int pos,
-                                              int lane) {
-    const L2Bytes b = l2_bytes_at(src, pos, n);
-    const L2Bytes b1 = l2_bytes_next(b);
-    if (lane == 0) {
-        l2_put_long(lTable, P.hashL(b.lo8()), pos, b);
-        l2_put_short(sTable, P.hashS(b1.lo8()), pos + 1, b1);
-    }
-}
-
-// A verified candidate at probe position p: backward extension (encode_l2.go:223-226) and forward
-// extension with byte tail (:239-254).  `own` = the bytes at p.  With a snapshot at hand (`cb` = the
-// byte before the candidate, `c1`, `c2` = its bytes 4..12 when `wide`) neither touches src[candidate]
-// unless the snapshot cannot decide.  Returns the match end; *back = bytes gained backwards.
-__device__ __forceinline__ int l2_extend(const uint8_t *src, int n, int p, const L2Bytes &own, int cand, bool snap,
-                                         uint32_t cb, bool wide, uint32_t c1, uint32_t c2, int nextEmit, int lane,
-                                         int *back) {
-    *back = 0;
-    if (p > nextEmit && cand > 0 && (!snap || own.back == cb)) *back = extend_backward(src, cand, p, nextEmit, lane);
-    int e;
-    if (wide) {
-        const uint64_t x = (uint64_t)(own.f[2] ^ c2) << 32 | (own.f[1] ^ c1);  // bytes 4..12 of both sides
-        e = x ? p + 4 + ((__ffsll((long long)x) - 1) >> 3) : extend_to_end(src, n, p + 12, cand + 12, lane);
-    } else {
-        e = extend_to_end(src, n, p + 4, cand + 4, lane);
-    }
-    return min(e, n);  // bytes past the block read as zero on both sides
-}
-
-struct L2GoHash {
-    bool small;
-    __device__ __forceinline__ uint32_t hashL(uint64_t u) const { return small ? hash6(u, 15) : hash7(u, 17); }
-    __device__ __forceinline__ uint32_t hashS(uint64_t u) const { return hash4(u, small ? 12 : 14); }
-};
-
 template <bool kSmall>
 __device__ int encode_l2_block(uint8_t *dst, const uint8_t *src, const int n, uint4 *lTable, uint2 *sTable,
                                uint32_t *rec_mem, const int lane) {
-    const L2GoHash P{kSmall};
+    using P = L2Params<kSmall>;
     L2Records q{rec_mem, 0, 0};
     const L2EmitGo ep{};
     int emitted = 0;  // nextEmit as the token writer sees it
-    const L2Bytes src0 = l2_bytes_at(src, 0, n);  // the bytes an untouched entry (candidate 0) stands for
+    const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
     const int sLimit = n - kInputMargin;
     const int dstLimit = n - (n >> 5) - 6;
     int nextEmit = 0;
     int s = 1;
+    uint64_t cv = ldg_u64_unaligned(src + s);
     int repeat = 1;
     int d = 0;
 
     for (;;) {
-        const int nextS = s + ((s - nextEmit) >> 7) + 1;  // :114
-        if (nextS > sLimit) break;
-        const L2Bytes ob = l2_bytes_at(src, s, n);
-        const uint64_t cv = ob.lo8();
-        const int minSrcPos = s - kMaxCopy3Offset + 1;  // :118
-        // lane 0: long(cv)  lane 1: short(cv)  lane 2: repeat  lane 3: long(cv>>8) (used only behind a short hit)
-        uint32_t h = 0, ex = 0, v0 = 0, v1 = 0, v2 = 0;
-        if (lane == 0) h = P.hashL(cv);
-        if (lane == 1) h = P.hashS(cv);
-        if (lane == 3) h = P.hashL(cv >> 8);
-        const uint32_t hL = __shfl_sync(kFullMask, h, 0);
-        if (lane == 0 || lane == 3) {
-            const uint4 e = lTable[h];
-            ex = e.x, v0 = e.y, v1 = e.z, v2 = e.w;
-        }
-        if (lane == 1) {
-            const uint2 e = sTable[h];
-            ex = e.x, v0 = e.y;
-        }
-        if (lane == 2) {  // :139
-            const uint64_t r = ldg_u64_unaligned(src + s - repeat);
-            v0 = (uint32_t)r, v1 = (uint32_t)(r >> 32);
-        }
-        int c = (int)(ex & 0xffffffu);
-        uint32_t cb = ex >> 24;
-        if (lane != 2 && c == 0) v0 = src0.f[0], v1 = src0.f[1], v2 = src0.f[2], cb = 0;
-        if (lane == 3 && h == hL) c = s, cb = ob.back, v0 = ob.f[0], v1 = ob.f[1], v2 = ob.f[2];  // lTable[hashL] = s precedes the s+1 probe (:124, :207)
-        __syncwarp();
-        if (lane == 0) l2_put_long(lTable, h, s, ob);
-        if (lane == 1) l2_put_short(sTable, h, s, ob);
-        const uint64_t v = (uint64_t)v1 << 32 | v0;
-        const uint64_t repeatMask = 0xffffffffull << 8;
-        bool f8 = false, f4 = false;
-        if (lane == 0) {
-            f8 = c > minSrcPos && cv == v;                            // :130
-            f4 = c >= minSrcPos && (uint32_t)cv == (uint32_t)v;       // :199
-        } else if (lane == 1) {
-            f4 = c >= minSrcPos && (uint32_t)cv == (uint32_t)v;       // :204
-        } else if (lane == 2) {
-            f4 = repeat > 0 && (cv & repeatMask) == (v & repeatMask); // :139
-        } else if (lane == 3) {
-            f4 = c > minSrcPos && (uint32_t)(cv >> 8) == (uint32_t)v; // :209
-        }
-        const unsigned m8 = __ballot_sync(kFullMask, f8);
-        const unsigned m4 = __ballot_sync(kFullMask, f4);
-
-        int from;  // lane that holds the winning candidate
-        if (m8 & 1u) {  // long candidate matches 8 bytes
-            from = 0;
-        } else if (m4 & 4u) {  // repeat at s+1 (:139-196)
-            int base = s + 1;
-            base -= extend_backward(src, base - repeat, base, nextEmit, lane);
-            const int cand = s - repeat + 4 + 1;
-            s = extend_to_end(src, n, s + 4 + 1, cand, lane);
-            q.push(base, repeat | 3 << 24, s, lane);  // :147 test, literals and the repeat token: emit_group
-            if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
-            nextEmit = s;
-            if (s >= sLimit) break;
-            // index in-between (:183-195); program order of one lane keeps "later write wins"
-            for (int index0 = base + 1, index1 = s - 2; index0 < index1; index0 += 2, index1 -= 2) {
-                l2_index_pair(P, lTable, sTable, src, n, index0, lane);
-                l2_index_pair(P, lTable, sTable, src, n, index1, lane);
+        int candidateL = 0;
+        int nextS = 0;
+        bool continue_outer = false;
+        for (;;) {
+            nextS = s + ((s - nextEmit) >> 7) + 1;  // :114
+            if (nextS > sLimit) goto emit_remainder;
+            const int minSrcPos = s - kMaxCopy3Offset + 1;  // :118
+            // lane 0: long(cv)  lane 1: short(cv)  lane 2: repeat  lane 3: long(cv>>8) (used only behind a short hit)
+            uint32_t h = 0;
+            int c = 0;
+            if (lane == 0) h = P::hashL(cv);
+            if (lane == 1) h = P::hashS(cv);
+            if (lane == 3) h = P::hashL(cv >> 8);
+            const uint32_t hL = __shfl_sync(kFullMask, h, 0);
+            uint64_t v = 0;  // the candidate's bytes: valLong / valShort (:127-128), load32 (:209)
+            if (lane == 0 || lane == 3) {
+                const uint4 e = lTable[h];
+                c = (int)e.x;
+                v = (uint64_t)e.z << 32 | e.y;
             }
+            if (lane == 1) {
+                const uint2 e = sTable[h];
+                c = (int)e.x;
+                v = e.y;
+            }
+            if (lane == 2) v = ldg_u64_unaligned(src + s - repeat);       // :139
+            if (lane != 2 && c == 0) v = src0;
+            if (lane == 3 && h == hL) c = s, v = cv;  // lTable[hashL] = s precedes the s+1 probe (:124, :207)
             __syncwarp();
-            continue;
-        } else if (m4 & 1u) {  // long candidate matches 4 bytes (:199)
-            from = 0;
-        } else if (m4 & 2u) {  // short candidate (:204-216): try the long table at s+1
-            if (lane == 3) l2_put_long(lTable, h, s + 1, l2_bytes_next(ob));
-            __syncwarp();
-            from = (m4 & 8u) ? 3 : 1;
-        } else {
-            s = nextS;  // :218
-            continue;
+            if (lane == 0) l2_put_long(lTable, h, s, cv);
+            if (lane == 1) l2_put_short(sTable, h, s, cv);
+            const uint64_t repeatMask = 0xffffffffull << 8;
+            bool f8 = false, f4 = false;
+            if (lane == 0) {
+                f8 = c > minSrcPos && cv == v;                            // :130
+                f4 = c >= minSrcPos && (uint32_t)cv == (uint32_t)v;       // :199
+            } else if (lane == 1) {
+                f4 = c >= minSrcPos && (uint32_t)cv == (uint32_t)v;       // :204
+            } else if (lane == 2) {
+                f4 = repeat > 0 && (cv & repeatMask) == (v & repeatMask); // :139
+            } else if (lane == 3) {
+                f4 = c > minSrcPos && (uint32_t)(cv >> 8) == (uint32_t)v; // :209
+            }
+            const unsigned m8 = __ballot_sync(kFullMask, f8);
+            const unsigned m4 = __ballot_sync(kFullMask, f4);
+
+            if (m8 & 1u) {  // long candidate matches 8 bytes
+                candidateL = __shfl_sync(kFullMask, c, 0);
+                break;
+            }
+            if (m4 & 4u) {  // repeat at s+1 (:139-196)
+                int base = s + 1;
+                base -= extend_backward(src, base - repeat, base, nextEmit, lane);
+                const int cand = s - repeat + 4 + 1;
+                s = extend_to_end(src, n, s + 4 + 1, cand, lane);
+                q.push(base, repeat | 3 << 24, s, lane);  // :147 test, literals and the repeat token: emit_group
+                if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
+                nextEmit = s;
+                if (s >= sLimit) goto emit_remainder;
+                // index in-between (:183-195)
+                l2_index_match<kL2OrderRepeat>(P(), lTable, sTable, src, base, s, lane);
+                cv = ldg_u64_unaligned(src + s);
+                continue;
+            }
+            if (m4 & 1u) {  // long candidate matches 4 bytes (:199)
+                candidateL = __shfl_sync(kFullMask, c, 0);
+                break;
+            }
+            if (m4 & 2u) {  // short candidate (:204-216): try the long table at s+1
+                if (lane == 3) l2_put_long(lTable, h, s + 1, ldg_u64_unaligned(src + s + 1));
+                __syncwarp();
+                if (m4 & 8u) {
+                    candidateL = __shfl_sync(kFullMask, c, 3);
+                    s++;
+                } else {
+                    candidateL = __shfl_sync(kFullMask, c, 1);
+                }
+                break;
+            }
+            cv = ldg_u64_unaligned(src + nextS);  // :218
+            s = nextS;
         }
 
-        // ---- a verified candidate: extend, record, index (:223-326) ----
-        const int p = from == 3 ? s + 1 : s;  // the probe's position
-        const int cand = __shfl_sync(kFullMask, c, from);
-        const uint32_t ccb = __shfl_sync(kFullMask, cb, from);
-        const uint32_t cc1 = __shfl_sync(kFullMask, v1, from), cc2 = __shfl_sync(kFullMask, v2, from);
-        int back;
-        const int e = l2_extend(src, n, p, from == 3 ? l2_bytes_next(ob) : ob, cand, true, ccb, from != 1, cc1, cc2, nextEmit,
-                                lane, &back);
-        const int base = p - back;  // the :229 test travels with the record
-        const int offset = p - cand;
-        s = e;
-        if (offset > 65535 && s - base <= 4 && repeat != offset) {  // :257-264
-            s = nextS + 1;
-            if (s >= sLimit) break;
-            continue;
+        {
+            const int back = extend_backward(src, candidateL, s, nextEmit, lane);  // :223-226
+            candidateL -= back;
+            s -= back;
         }
-        q.push(base, offset, s, lane);  // :266-289 and the :297 test: emit_group
-        if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
-        repeat = offset;
-        nextEmit = s;
-        if (s >= sLimit) break;  // :293
+        {   // the :229 test travels with the record
+            const int base = s;
+            const int offset = base - candidateL;
+            s = extend_to_end(src, n, s + 4, candidateL + 4, lane);  // :239-254
 
-        // index short & long (:303-326)
-        int index0 = base + 1;
-        int index1 = s - 2;
-        l2_index_pair(P, lTable, sTable, src, n, index0, lane);
-        l2_index_pair(P, lTable, sTable, src, n, index1, lane);
-        index0 += 1;
-        index1 -= 1;
-        // sparse long-table indexing of the interior; serial order preserved by one lane
-        for (int index2 = (index0 + index1 + 1) >> 1; index2 < index1; index0 += 2, index2 += 2) {
-            l2_index_long(P, lTable, src, n, index0, lane);
-            l2_index_long(P, lTable, src, n, index2, lane);
+            if (offset > 65535 && s - base <= 4 && repeat != offset) {  // :257-264
+                s = nextS + 1;
+                if (s >= sLimit) goto emit_remainder;
+                cv = ldg_u64_unaligned(src + s);
+                continue_outer = true;
+            }
+            if (!continue_outer) {
+                q.push(base, offset, s, lane);  // :266-289 and the :297 test: emit_group
+                if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
+                repeat = offset;
+                nextEmit = s;
+                if (s >= sLimit) goto emit_remainder;  // :293
+
+                // index short & long (:303-326)
+                l2_index_match<kL2OrderGo>(P(), lTable, sTable, src, base, s, lane);
+                cv = ldg_u64_unaligned(src + s);
+            }
         }
-        __syncwarp();
     }
 
-    // emit_remainder :329-337
+emit_remainder:  // :329-337
     if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, true)) return 0;
     if (nextEmit < n) {
         if (d + n - nextEmit > dstLimit) return 0;
@@ -423,7 +389,7 @@ struct BetterAsm2MB {
 template <class C>
 __device__ int encode_l2_asm_block(const C P, uint8_t *dst, const uint8_t *src, const int n,
                                    uint4 *lTable, uint2 *sTable, uint32_t *rec_mem, const int lane) {
-    const L2Bytes src0 = l2_bytes_at(src, 0, n);  // the bytes an untouched entry (candidate 0) stands for
+    const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
     L2Records q{rec_mem, 0, 0};
     const L2EmitAsm ep{P.ovh, P.quirk};
     int emitted = 0;  // nextEmit as the token writer sees it
@@ -439,42 +405,36 @@ __device__ int encode_l2_asm_block(const C P, uint8_t *dst, const uint8_t *src, 
         const uint32_t skip = (uint32_t)(s - nextEmit) >> P.skipLog;
         const int nextS = (P.maxSkip == 0 || skip <= (uint32_t)(P.maxSkip - 1)) ? s + (int)skip + 1 : s + P.maxSkip;
         if (nextS >= sLimit) break;
-        const L2Bytes ob = l2_bytes_at(src, s, n);
-        const uint64_t cv = ob.lo8();
+        const uint64_t cv = ldg_u64_unaligned(src + s);
         const int minPos = s - kMaxCopy3Offset + 2;
         // lane 0: long(cv)  lane 1: short(cv)  lane 2: repeat  lane 3: long(cv>>8) (used only behind a short hit)
-        uint32_t h = 0, ex = 0, v0 = 0, v1 = 0, v2 = 0;
+        uint32_t h = 0;
+        int c = 0;
         if (lane == 0) h = P.hashL(cv);
         if (lane == 1) h = P.hashS(cv);
         if (lane == 3) h = P.hashL(cv >> 8);
         const uint32_t hL = __shfl_sync(kFullMask, h, 0);
+        uint64_t v = 0;  // the candidate's bytes
         if (lane == 0 || lane == 3) {
             const uint4 e = lTable[h];
-            ex = e.x, v0 = e.y, v1 = e.z, v2 = e.w;
+            c = (int)e.x;
+            v = (uint64_t)e.z << 32 | e.y;
         }
         if (lane == 1) {
             const uint2 e = sTable[h];
-            ex = e.x, v0 = e.y;
+            c = (int)e.x;
+            v = e.y;
         }
-        if (lane == 2) {
-            const uint64_t r = ldg_u64_unaligned(src + s - repeat);
-            v0 = (uint32_t)r, v1 = (uint32_t)(r >> 32);
-        }
-        int c = (int)(ex & 0xffffffu);
-        uint32_t cb = ex >> 24;
-        bool snap = true;  // the entry's bytes are the candidate's bytes
-        if (lane != 2 && c == 0) v0 = src0.f[0], v1 = src0.f[1], v2 = src0.f[2], cb = 0;
-        if (lane == 3 && h == hL) c = s, cb = ob.back, v0 = ob.f[0], v1 = ob.f[1], v2 = ob.f[2];  // lTab[hash0] = s is stored before the s+1 probe reads
+        if (lane == 2) v = ldg_u64_unaligned(src + s - repeat);
+        if (lane != 2 && c == 0) v = src0;
+        if (lane == 3 && h == hL) c = s, v = cv;  // lTab[hash0] = s is stored before the s+1 probe reads
         __syncwarp();
-        if (lane == 0) l2_put_long(lTable, h, s, ob);
-        if (lane == 1) l2_put_short(sTable, h, s, ob);
+        if (lane == 0) l2_put_long(lTable, h, s, cv);
+        if (lane == 1) l2_put_short(sTable, h, s, cv);
         if (P.clamp && lane != 2 && lane < 4 && c <= minPos) {  // CMOVLLE: compared (and matched) at the clamped position
             c = minPos;
-            const uint64_t r = ldg_u64_unaligned(src + c);  // not the entry's position any more: read the source (8 MiB class only)
-            v0 = (uint32_t)r, v1 = (uint32_t)(r >> 32);
-            snap = false;
+            v = ldg_u64_unaligned(src + c);  // not the entry's position any more: read the source (8 MiB class only)
         }
-        const uint64_t v = (uint64_t)v1 << 32 | v0;
         bool f8 = false, f4 = false;
         if (lane == 0) {
             f8 = cv == v;
@@ -488,11 +448,10 @@ __device__ int encode_l2_asm_block(const C P, uint8_t *dst, const uint8_t *src, 
         }
         const unsigned m8 = __ballot_sync(kFullMask, f8);
         const unsigned m4 = __ballot_sync(kFullMask, f4);
-        const unsigned msnap = __ballot_sync(kFullMask, snap);
 
-        int from;  // lane that holds the winning candidate
+        int candidate;
         if (m8 & 1u) {
-            from = 0;
+            candidate = __shfl_sync(kFullMask, c, 0);
         } else if (m4 & 4u) {  // repeat at s+1 (gen.go:1445-1622)
             int base = s + 1;
             base -= extend_backward(src, base - repeat, base, nextEmit, lane);
@@ -501,35 +460,33 @@ __device__ int encode_l2_asm_block(const C P, uint8_t *dst, const uint8_t *src, 
             if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
             nextEmit = s;
             if (s >= sLimit) break;
-            for (int i0 = base + 1, i1 = s - 2; i0 < i1; i0 += 2, i1 -= 2) {
-                l2_index_pair(P, lTable, sTable, src, n, i0, lane);
-                l2_index_pair(P, lTable, sTable, src, n, i1, lane);
-            }
-            __syncwarp();
+            l2_index_match<kL2OrderRepeat>(P, lTable, sTable, src, base, s, lane);
             continue;
         } else if (m4 & 1u) {
-            from = 0;
+            candidate = __shfl_sync(kFullMask, c, 0);
         } else if (m4 & 2u) {  // short match: try the long table at s+1 (gen.go:1665-1687)
-            if (lane == 3) l2_put_long(lTable, h, s + 1, l2_bytes_next(ob));
+            if (lane == 3) l2_put_long(lTable, h, s + 1, ldg_u64_unaligned(src + s + 1));
             __syncwarp();
-            from = (m4 & 8u) ? 3 : 1;
+            if (m4 & 8u) {
+                candidate = __shfl_sync(kFullMask, c, 3);
+                s++;
+            } else {
+                candidate = __shfl_sync(kFullMask, c, 1);
+            }
         } else {
             s = nextS;
             continue;
         }
 
         // ---- candidate_match (gen.go:1692-1918) ----
-        const int p = from == 3 ? s + 1 : s;  // the probe's position
-        const int cand = __shfl_sync(kFullMask, c, from);
-        const uint32_t ccb = __shfl_sync(kFullMask, cb, from);
-        const uint32_t cc1 = __shfl_sync(kFullMask, v1, from), cc2 = __shfl_sync(kFullMask, v2, from);
-        const bool csnap = (msnap >> from) & 1u;
-        int back;
-        const int e = l2_extend(src, n, p, from == 3 ? l2_bytes_next(ob) : ob, cand, csnap, ccb, csnap && from != 1, cc1, cc2,
-                                nextEmit, lane, &back);
-        const int base = p - back;  // the gen.go:1720-1737 test travels with the record
-        const int offset = p - cand;
-        s = e;
+        {
+            const int back = extend_backward(src, candidate, s, nextEmit, lane);
+            candidate -= back;
+            s -= back;
+        }
+        const int base = s;  // the gen.go:1720-1737 test travels with the record
+        const int offset = base - candidate;
+        s = extend_to_end(src, n, s + 4, candidate + 4, lane);
         if (P.far3 && s - base == 4 && offset > kMaxCopy2Offset && offset != repeat) {  // gen.go:1786-1801
             s = nextS + 1;
             continue;
@@ -539,25 +496,7 @@ __device__ int encode_l2_asm_block(const C P, uint8_t *dst, const uint8_t *src, 
         if (!q.flush(ep, dst, src, d, emitted, lane, sLimit, dstLimit, false)) return 0;
         nextEmit = s;
         if (s >= sLimit) break;
-        {   // index the match interior (gen.go:1921-1978); one lane keeps "later write wins"
-            int i0 = base + 1, i1 = s - 2;
-            const L2Bytes a0 = l2_bytes_at(src, i0, n), b0 = l2_bytes_at(src, i1, n);
-            const L2Bytes a1 = l2_bytes_next(a0), b1 = l2_bytes_next(b0);
-            if (lane == 0) {
-                l2_put_long(lTable, P.hashL(a0.lo8()), i0, a0);
-                l2_put_long(lTable, P.hashL(b0.lo8()), i1, b0);
-                l2_put_short(sTable, P.hashS(a1.lo8()), i0 + 1, a1);
-                l2_put_short(sTable, P.hashS(b1.lo8()), i1 + 1, b1);
-            }
-            int i2 = (i0 + i1 + 1) >> 1;
-            i0 += 1;
-            i1 -= 1;
-            for (; i2 < i1; i0 += 2, i2 += 2) {
-                l2_index_long(P, lTable, src, n, i0, lane);
-                l2_index_long(P, lTable, src, n, i2, lane);
-            }
-            __syncwarp();
-        }
+        l2_index_match<kL2OrderAsm>(P, lTable, sTable, src, base, s, lane);  // gen.go:1921-1978
     }
 
     // emit_remainder (gen.go:1980-2017): the bail test runs even when nothing is left

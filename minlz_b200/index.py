@@ -316,7 +316,9 @@ def IndexStream(r):
         if ctype in (st.CHUNK_LEGACY, st.CHUNK_MINLZ, st.CHUNK_MINLZ_COMP_CRC):
             # stream chunks carry the block without its leading 0x00 (writer.go:677)
             body = buf[4:]
-            dlen = DecodedLen(b"\x00" + body) if ctype != st.CHUNK_LEGACY else _snappy_len(body)
+            # index.go:493 calls DecodedLen on the chunk body, which starts with the uvarint and so
+            # takes the plain-varint branch of isMinLZ (decode.go:128-133): no block-header checks
+            dlen = _snappy_len(body)
             if dlen > st.MAX_BLOCK_SIZE:
                 raise ErrCorrupt()
             n2 = dlen
@@ -345,6 +347,8 @@ def _snappy_len(body):
     for i, c in enumerate(body[:10]):
         v |= (c & 0x7F) << sh
         if c < 0x80:
+            if v > 0xFFFFFFFF:
+                raise ErrCorrupt()
             return v
         sh += 7
     raise ErrCorrupt()
