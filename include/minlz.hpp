@@ -189,7 +189,12 @@ inline std::pair<bool, int64_t> IsMinLZ(const Bytes &b) {
 
 // decode.go:50-78 (MinLZ blocks; a first byte != 0 is Snappy/S2 territory: Err::Unsupported)
 inline Bytes Decode(const uint8_t *block, size_t n) {
-    const int64_t dlen = DecodedLen(block, n);
+    // nothing is allocated before the block is known to be MinLZ of a legal size
+    int ok = 0;
+    int64_t dlen = 0;
+    detail::check(mzcu_is_minlz(detail::ptr(block, n), n, &ok, &dlen));
+    if (!ok) throw Error(Err::Unsupported, "minlz: unsupported input");
+    if (dlen > MaxBlockSize) throw Error(Err::TooLarge, "minlz: decoded block is too large");
     Bytes out(size_t(std::max<int64_t>(dlen, 1)));
     const int64_t r = mzcu_decode(out.data(), size_t(dlen), detail::ptr(block, n), n);
     if (r == MZCU_ERR_CORRUPT) {
