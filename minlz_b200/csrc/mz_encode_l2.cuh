@@ -348,6 +348,7 @@ emit_remainder:  // :329-337
 // candidates clamped to s-2162685 in the 8 MiB class (gen.go:1396-1419), per-class
 // tables / hashes and the 64 KiB literal quirk (gen.go:2193-2200).
 struct BetterAsmClass {
+    static constexpr bool kGo = false;
     int lBits, sBits, skipLog, lHashBytes, maxSkip, outMargin, inMargin, ovh;
     bool quirk, far3, clamp;
     __device__ __forceinline__ uint32_t hashL(uint64_t u) const { return lHashBytes == 7 ? hash7(u, lBits) : hash6(u, lBits); }
@@ -379,6 +380,7 @@ struct BetterAsmClass {
 // The class of the benchmark's block sizes (512 KiB+1 .. 2 MiB, encodeBetterBlockAsm2MB:
 // gen.go:80) with compile-time parameters; every other class runs on the runtime struct above.
 struct BetterAsm2MB {
+    static constexpr bool kGo = false;
     static constexpr int lBits = 17, sBits = 14, skipLog = 7, lHashBytes = 7, maxSkip = 100, outMargin = 17,
                          inMargin = 17, ovh = 4;
     static constexpr bool quirk = false, far3 = true, clamp = false;
@@ -506,6 +508,299 @@ __device__ int encode_l2_asm_block(const C P, uint8_t *dst, const uint8_t *src, 
     return d;
 }
 
+// ---- the probe-window walk ------------------------------------------------------
+// A step of the LevelBalanced walk is one DRAM round trip (its table probes) plus ~1 us of
+// dependent instructions, 123 k times per 1 MiB block, and the profile of the step-at-a-time walk
+// above says where the time goes: 41 % waiting for the probes, 17 % for other loads, the rest on
+// the warp's own instruction chain (profiles/r02_ncu_encode_l2_step_walk.txt).  This walk probes a
+// WINDOW of 32 consecutive positions per round trip -- lane j holds, for position wb + j, its 8
+// source bytes, both hashes and both table entries -- and steps through the window on the cached
+// entries: 4.3 steps per round trip on the benchmark's blocks (profiles/r02_l2_walk_sim.txt).
+// Exactness: every table insert the walk performs while a window is live is also applied to the
+// window ("patch"), so a cached entry always equals what a load would return at that moment:
+//   * the step's own inserts (long[s], short[s]) and the deferred long[s+1] patch the later lanes
+//     that share the slot (found once per window with match.any on the hashes; rare);
+//   * the inserts of a match's interior are positions of the window itself, so their hashes are
+//     the lanes' own: every lane knows in closed form whether its position was inserted and with
+//     which serial rank, and a later lane takes the highest-ranked inserted lane of its hash group;
+//   * inserts outside the window end it (behind it: the window is reloaded; beyond it: the walk
+//     has left it anyway).
+// The repeat check needs 4 bytes at p + 1 - repeat; they are loaded per window and again after
+// every match (the repeat offset changed), off the critical path when the next step hits on 8 bytes.
+#ifndef MZ_L2_REPLAY
+#define MZ_L2_REPLAY 1
+#endif
+
+template <bool kSmall>
+struct L2GoClass {
+    static constexpr bool kGo = true;
+    static constexpr int skipLog = 7, maxSkip = 0, ovh = 0, inMargin = kInputMargin, outMargin = 6;
+    static constexpr bool quirk = false, far3 = true, clamp = false;
+    __device__ __forceinline__ uint32_t hashL(uint64_t u) const { return kSmall ? hash6(u, 15) : hash7(u, 17); }
+    __device__ __forceinline__ uint32_t hashS(uint64_t u) const { return hash4(u, kSmall ? 12 : 14); }
+};
+
+// membership and serial rank of position p among the inserts of one match (see l2_index_match)
+template <int kOrder>
+__device__ __forceinline__ void l2_insert_rank(int p, int base, int e, int *rankL, int *rankS) {
+    int rl = -1, rs = -1;
+    if (kOrder == kL2OrderRepeat) {
+        const int span = e - base - 3;
+        const int J = span > 0 ? (span + 3) >> 2 : 0;
+        const int a = p - (base + 1), b = (e - 2) - p;
+        if (a >= 0 && !(a & 1) && (a >> 1) < J) rl = 4 * (a >> 1);
+        if (b >= 0 && !(b & 1) && (b >> 1) < J) rl = max(rl, 4 * (b >> 1) + 2);
+        const int a1 = a - 1, b1 = b + 1;  // short inserts sit one position behind a long one
+        if (a1 >= 0 && !(a1 & 1) && (a1 >> 1) < J) rs = 4 * (a1 >> 1) + 1;
+        if (b1 >= 0 && !(b1 & 1) && (b1 >> 1) < J) rs = max(rs, 4 * (b1 >> 1) + 3);
+    } else {
+        const int mid = (base + 2 + e - 3 + 1) >> 1;
+        const int left = e - 3 - mid;
+        const int K = left > 0 ? (left + 1) >> 1 : 0;
+        if (p == base + 1) rl = 0;
+        if (p == e - 2) rl = max(rl, kOrder == kL2OrderAsm ? 1 : 2);
+        const int a = p - (base + 2), b = p - mid;
+        if (a >= 0 && !(a & 1) && (a >> 1) < K) rl = max(rl, 4 + 2 * (a >> 1));
+        if (b >= 0 && !(b & 1) && (b >> 1) < K) rl = max(rl, 5 + 2 * (b >> 1));
+        if (p == base + 2) rs = kOrder == kL2OrderAsm ? 2 : 1;
+        if (p == e - 1) rs = max(rs, 3);
+    }
+    *rankL = rl;
+    *rankS = rs;
+}
+
+template <class C>
+__device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const int n, uint4 *lTable, uint2 *sTable,
+                              uint32_t *rec_mem, const int lane) {
+    constexpr bool kGo = C::kGo;
+    const uint64_t src0 = ldg_u64_unaligned(src);  // the bytes an untouched entry (candidate 0) stands for
+    L2Records q{rec_mem, 0, 0};
+    const L2EmitGo epg{};
+    const L2EmitAsm epa{P.ovh, P.quirk};
+    int emitted = 0;  // nextEmit as the token writer sees it
+    const int sLimit = kGo ? n - kInputMargin : n - P.inMargin;                      // :65 / gen.go:1272-1282
+    const int dstLimit = kGo ? n - (n >> 5) - 6 : n - P.outMargin - (n >> 5);        // :92 / gen.go:1284-1297
+    int nextEmit = 0, s = 1, repeat = 1, d = 0;
+    auto flush = [&](bool all) -> bool {
+        return kGo ? q.flush(epg, dst, src, d, emitted, lane, sLimit, dstLimit, all)
+                   : q.flush(epa, dst, src, d, emitted, lane, sLimit, dstLimit, all);
+    };
+
+    // ---- the window: lane j <-> position wb + j ----
+    int wb = 0;
+    bool wvalid = false;
+    int repw = 0;          // the repeat offset rep4 was loaded for (0 = none)
+    uint64_t cv = 0;       // src[p .. p+8)
+    uint32_t hL = 0, hS = 0;
+    int cL = 0, cS = 0;    // cached table entries of my position's slots
+    uint64_t vL = 0;
+    uint32_t vS = 0, rep4 = 0;
+    unsigned sameL = 0, sameS = 0;
+    const unsigned self = 1u << lane;
+
+    for (;;) {
+        // ---- next position (encode_l2.go:114-117; gen.go:1307-1354) ----
+        const uint32_t skip = (uint32_t)(s - nextEmit) >> P.skipLog;
+        const int nextS = (P.maxSkip == 0 || skip <= (uint32_t)(P.maxSkip - 1)) ? s + (int)skip + 1 : s + P.maxSkip;
+        if (kGo ? nextS > sLimit : nextS >= sLimit) break;
+
+        // ---- (re)load the window when the step and its s+1 probe are not inside it ----
+        int L = s - wb;
+        if (!wvalid || L < 0 || L > 30) {
+            __syncwarp();  // the stores of earlier inserts are ordered before these loads
+            wb = s;
+            L = 0;
+            wvalid = true;
+            const int p = wb + lane;
+            cv = ld64_clamped(src, p, n);
+            hL = P.hashL(cv);
+            hS = P.hashS(cv);
+            const uint4 el = lTable[hL];
+            const uint2 es = sTable[hS];
+            repw = repeat;
+            rep4 = (p + 5 <= n && p + 1 >= repeat) ? ldg_u32_unaligned(src + p + 1 - repeat) : 0;
+            cL = (int)el.x;
+            vL = (uint64_t)el.z << 32 | el.y;
+            cS = (int)es.x;
+            vS = es.y;
+            if (cL == 0) vL = src0;
+            if (cS == 0) vS = (uint32_t)src0;
+            sameL = __match_any_sync(kFullMask, hL);
+            sameS = __match_any_sync(kFullMask, hS);
+        }
+        const int p = wb + lane;
+        if (repw != repeat) {  // the repeat offset changed since the bytes for its check were loaded
+            repw = repeat;
+            rep4 = (p + 5 <= n && p + 1 >= repeat) ? ldg_u32_unaligned(src + p + 1 - repeat) : 0;
+        }
+
+        // ---- every lane answers for its own position (encode_l2.go:118-216; gen.go:1356-1690) ----
+        int kL = cL, kS = cS;  // candidates as the compares see them
+        uint64_t wL = vL;
+        uint32_t wS = vS;
+        int kN = cL;           // ... and as the long probe at s+1 of the step at p-1 sees them
+        uint64_t wN = vL;
+        bool f8, f4l, f4s, fr, fn;
+        if (kGo) {
+            const int minSrcPos = p - kMaxCopy3Offset + 1;  // :118
+            f8 = kL > minSrcPos && cv == wL;                                   // :130
+            f4l = kL >= minSrcPos && (uint32_t)cv == (uint32_t)wL;             // :199
+            f4s = kS >= minSrcPos && (uint32_t)cv == wS;                       // :204
+            fr = repeat > 0 && (uint32_t)(cv >> 8) == rep4;                    // :139
+            fn = kN > minSrcPos - 1 && (uint32_t)cv == (uint32_t)wN;           // :209 (minSrcPos of the step at p-1)
+        } else {
+            if (P.clamp) {  // CMOVLLE: compared (and matched) at the clamped position (8 MiB class only)
+                const int minPos = p - kMaxCopy3Offset + 2;
+                if (kL <= minPos) kL = minPos, wL = ldg_u64_unaligned(src + kL);
+                if (kS <= minPos) kS = minPos, wS = ldg_u32_unaligned(src + kS);
+                if (kN <= minPos - 1) kN = minPos - 1, wN = ldg_u64_unaligned(src + kN);
+            }
+            f8 = cv == wL;
+            f4l = (uint32_t)cv == (uint32_t)wL;
+            f4s = (uint32_t)cv == wS;
+            fr = (uint32_t)(cv >> 8) == rep4;
+            fn = (uint32_t)cv == (uint32_t)wN;
+        }
+        const unsigned m8 = __ballot_sync(kFullMask, f8), m4l = __ballot_sync(kFullMask, f4l),
+                       m4s = __ballot_sync(kFullMask, f4s), mr = __ballot_sync(kFullMask, fr);
+        unsigned mn = __ballot_sync(kFullMask, fn);
+        const unsigned dupL = __ballot_sync(kFullMask, (sameL & ~self) != 0), dupS = __ballot_sync(kFullMask, (sameS & ~self) != 0);
+        const unsigned bitL = 1u << L;
+
+        // ---- the step's inserts: long[s] = s, short[s] = s (before the compares' consequences, :124-125) ----
+        if (lane == L) {
+            l2_put_long(lTable, hL, s, cv);
+            l2_put_short(sTable, hS, s, cv);
+        }
+        if ((dupL | dupS) & bitL) {  // later lanes of the window share a slot with s: they now see s there
+            const uint64_t cvs = __shfl_sync(kFullMask, cv, L);
+            const unsigned gl = __shfl_sync(kFullMask, sameL, L), gs = __shfl_sync(kFullMask, sameS, L);
+            if (lane > L && (gl & self)) cL = s, vL = cvs;
+            if (lane > L && (gs & self)) cS = s, vS = (uint32_t)cvs;
+            if (gl & (bitL << 1)) {  // the s+1 probe reads lTable after lTable[hashL] = s (:207)
+                bool f = false;
+                if (lane == L + 1) {
+                    int k2 = cL;
+                    uint64_t w2 = vL;
+                    if (!kGo && P.clamp && k2 <= p - 1 - kMaxCopy3Offset + 2) k2 = p - 1 - kMaxCopy3Offset + 2, w2 = ldg_u64_unaligned(src + k2);
+                    f = (kGo ? k2 > p - 1 - kMaxCopy3Offset + 1 : true) && (uint32_t)cv == (uint32_t)w2;
+                    kN = k2;
+                }
+                mn = (mn & ~(bitL << 1)) | (__ballot_sync(kFullMask, f) & (bitL << 1));
+            }
+        }
+
+        int kind;  // 0: long candidate of s, 1: short candidate of s, 2: long candidate of s+1
+        if (m8 & bitL) {
+            kind = 0;
+        } else if (mr & bitL) {  // repeat at s+1 (:139-196; gen.go:1445-1622)
+            int base = s + 1;
+            base -= extend_backward(src, base - repeat, base, nextEmit, lane);
+            s = extend_to_end(src, n, s + 5, s + 5 - repeat, lane);
+            q.push(base, repeat | 3 << 24, s, lane);
+            if (!flush(false)) return 0;
+            nextEmit = s;
+            if (s >= sLimit) break;
+            l2_index_match<kL2OrderRepeat>(P, lTable, sTable, src, base, s, lane);
+            if (s - wb <= 30) {
+                if (base + 1 < wb) {
+                    wvalid = false;  // inserts behind the window: their hashes are not at hand
+                } else {
+                    int rl, rs;
+                    l2_insert_rank<kL2OrderRepeat>(p, base, s, &rl, &rs);
+                    const unsigned QL = __ballot_sync(kFullMask, rl >= 0), QS = __ballot_sync(kFullMask, rs >= 0);
+                    unsigned candl = p >= s ? (QL & sameL) : 0u, cands = p >= s ? (QS & sameS) : 0u;
+                    int bestl = -1, bests = -1;
+                    while (__any_sync(kFullMask, (candl | cands) != 0)) {
+                        const int jl = candl ? __ffs(candl) - 1 : lane, js = cands ? __ffs(cands) - 1 : lane;
+                        const int kl = __shfl_sync(kFullMask, rl, jl) << 5 | jl, ks = __shfl_sync(kFullMask, rs, js) << 5 | js;
+                        if (candl) bestl = max(bestl, kl), candl &= candl - 1;
+                        if (cands) bests = max(bests, ks), cands &= cands - 1;
+                    }
+                    const uint64_t cvl = __shfl_sync(kFullMask, cv, bestl >= 0 ? bestl & 31 : lane);
+                    const uint64_t cvs2 = __shfl_sync(kFullMask, cv, bests >= 0 ? bests & 31 : lane);
+                    if (bestl >= 0) cL = wb + (bestl & 31), vL = cvl;
+                    if (bests >= 0) cS = wb + (bests & 31), vS = (uint32_t)cvs2;
+                }
+            }
+            continue;
+        } else if (m4l & bitL) {
+            kind = 0;
+        } else if (m4s & bitL) {  // short candidate: try the long table at s+1 (:204-216; gen.go:1665-1687)
+            // lTable[hashL(s+1)] = s+1, whatever the s+1 compare says
+            if (lane == L + 1) l2_put_long(lTable, hL, s + 1, cv);
+            if (dupL & (bitL << 1)) {
+                const uint64_t cv1 = __shfl_sync(kFullMask, cv, L + 1);
+                const unsigned g1 = __shfl_sync(kFullMask, sameL, L + 1);
+                if (lane > L + 1 && (g1 & self)) cL = s + 1, vL = cv1;
+            }
+            kind = (mn & (bitL << 1)) ? 2 : 1;
+        } else {
+            s = nextS;  // :218
+            continue;
+        }
+
+        // ---- a verified candidate (:223-326; gen.go:1692-1978) ----
+        const int from = kind == 2 ? L + 1 : L;
+        int candidate = __shfl_sync(kFullMask, kind == 1 ? kS : (kind == 2 ? kN : kL), from);
+        if (kind == 2) s++;
+        {
+            const int back = extend_backward(src, candidate, s, nextEmit, lane);
+            candidate -= back;
+            s -= back;
+        }
+        const int base = s;
+        const int offset = base - candidate;
+        s = extend_to_end(src, n, s + 4, candidate + 4, lane);
+        if (kGo ? (offset > 65535 && s - base <= 4 && repeat != offset)                              // :257-264
+                : (P.far3 && s - base == 4 && offset > kMaxCopy2Offset && offset != repeat)) {       // gen.go:1786-1801
+            s = nextS + 1;
+            if (kGo && s >= sLimit) break;
+            continue;
+        }
+        repeat = offset;
+        q.push(base, offset, s, lane);
+        if (!flush(false)) return 0;
+        nextEmit = s;
+        if (s >= sLimit) break;
+        l2_index_match<kGo ? kL2OrderGo : kL2OrderAsm>(P, lTable, sTable, src, base, s, lane);
+        if (s - wb <= 30) {  // the window lives on: apply the match's inserts to it
+            if (base + 1 < wb) {
+                wvalid = false;
+            } else {
+                int rl, rs;
+                l2_insert_rank<kGo ? kL2OrderGo : kL2OrderAsm>(p, base, s, &rl, &rs);
+                const unsigned QL = __ballot_sync(kFullMask, rl >= 0), QS = __ballot_sync(kFullMask, rs >= 0);
+                unsigned candl = p >= s ? (QL & sameL) : 0u, cands = p >= s ? (QS & sameS) : 0u;
+                int bestl = -1, bests = -1;
+                while (__any_sync(kFullMask, (candl | cands) != 0)) {
+                    const int jl = candl ? __ffs(candl) - 1 : lane, js = cands ? __ffs(cands) - 1 : lane;
+                    const int kl = __shfl_sync(kFullMask, rl, jl) << 5 | jl, ks = __shfl_sync(kFullMask, rs, js) << 5 | js;
+                    if (candl) bestl = max(bestl, kl), candl &= candl - 1;
+                    if (cands) bests = max(bests, ks), cands &= cands - 1;
+                }
+                const uint64_t cvl = __shfl_sync(kFullMask, cv, bestl >= 0 ? bestl & 31 : lane);
+                const uint64_t cvs2 = __shfl_sync(kFullMask, cv, bests >= 0 ? bests & 31 : lane);
+                if (bestl >= 0) cL = wb + (bestl & 31), vL = cvl;
+                if (bests >= 0) cS = wb + (bests & 31), vS = (uint32_t)cvs2;
+            }
+        }
+    }
+
+    // emit_remainder (:329-337; gen.go:1980-2017: there the bail test runs even when nothing is left)
+    if (!flush(true)) return 0;
+    if (kGo) {
+        if (nextEmit < n) {
+            if (d + n - nextEmit > dstLimit) return 0;
+            d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane);
+        }
+    } else {
+        if (d + (n - nextEmit) + P.ovh >= dstLimit) return 0;
+        d += emit_literal(dst + d, src + nextEmit, n - nextEmit, lane, P.quirk);
+    }
+    return d;
+}
+
 __global__ void __launch_bounds__(kEncL2Warps * 32)
 encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                      const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
@@ -531,9 +826,15 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
             for (int i = lane; i < (1 << cls.sBits) / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
+#if MZ_L2_REPLAY
+            res = (n > (512 << 10) && n <= (2 << 20))
+                      ? encode_l2_walk(BetterAsm2MB(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
+                      : encode_l2_walk(cls, dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+#else
             res = (n > (512 << 10) && n <= (2 << 20))
                       ? encode_l2_asm_block(BetterAsm2MB(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
                       : encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+#endif
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
@@ -568,8 +869,13 @@ encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
             for (int i = lane; i < sents / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
+#if MZ_L2_REPLAY
+            res = small ? encode_l2_walk(L2GoClass<true>(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
+                        : encode_l2_walk(L2GoClass<false>(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+#else
             res = small ? encode_l2_block<true>(dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
                         : encode_l2_block<false>(dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+#endif
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
         __syncwarp();
