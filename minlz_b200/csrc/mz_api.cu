@@ -688,6 +688,9 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
     uint64_t *d_sbeg = w->d_tab, *d_send = w->d_tab + T, *d_dbeg = w->d_tab + 2 * T, *d_poff = w->d_tab + 3 * T;
     uint32_t *d_out = reinterpret_cast<uint32_t *>(w->d_tab + 4 * T);
     uint32_t *d_crc = d_out + T;  // second half of the 5th table row
+    // checksums travel through the pinned mirror: a D2H into the caller's (possibly pageable) array
+    // would block the host until the kernels before it are done and serialise the chunk pipelines
+    uint32_t *h_crc = reinterpret_cast<uint32_t *>(w->h_tab + 4 * T) + T;
     size_t dof = 0;
     for (int i = 0; i < nblk; i++) {
         h_sbeg[i] = src_off[i] - base;
@@ -750,7 +753,7 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
                 if (crc_out) {  // checksum of the uncompressed blocks (writer.go:672)
                     rc = launch_crc(device, nblk, w->d_src, d_sbeg, d_send, d_crc, w->stream);
                     if (rc == MZCU_OK)
-                        CU_TRY(cudaMemcpyAsync(crc_out, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                        CU_TRY(cudaMemcpyAsync(h_crc, d_crc, (size_t)nblk * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                                w->stream));
                 }
                 if (rc == MZCU_OK) rc = launch_pack(device, nblk, w->d_dst, d_dbeg, d_out, w->d_src, d_poff, w->stream);
@@ -764,6 +767,7 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
                 if (packed > dst_cap) return fail(MZCU_ERR_DST_TOO_SMALL, "packed output exceeds capacity %zu", dst_cap);
                 if (packed) CU_TRY(cudaMemcpyAsync(dst, w->d_src, packed, cudaMemcpyDeviceToHost, w->stream));
                 for (int i = 0; i <= nblk; i++) dst_off_out[i] = h_poff[i];
+                if (crc_out) memcpy(crc_out, h_crc, (size_t)nblk * sizeof(uint32_t));  // landed before the sync above
                 CU_TRY(cudaEventRecord(w->ev1, w->stream));
                 CU_TRY(cudaStreamSynchronize(w->stream));
                 cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
@@ -805,7 +809,7 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
         rc = launch_pack(device, m, w->d_dst, d_dbeg + f, d_out + f, w->d_src + cb, d_poff + f + c, cs);
         if (rc) return rc;
         CU_TRY(cudaMemcpyAsync(h_poff + f + c, d_poff + f + c, (size_t)(m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, cs));
-        if (crc_out) CU_TRY(cudaMemcpyAsync(crc_out + f, d_crc + f, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+        if (crc_out) CU_TRY(cudaMemcpyAsync(h_crc + f, d_crc + f, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
     }
     size_t host_pos = 0;
     for (int c = 0; c < nchunks; c++) {
@@ -828,6 +832,7 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
     }
     CU_TRY(cudaEventRecord(w->ev1, w->stream));
     CU_TRY(cudaStreamSynchronize(w->stream));
+    if (crc_out) memcpy(crc_out, h_crc, (size_t)nblk * sizeof(uint32_t));
     cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
     return MZCU_OK;
 }
@@ -874,6 +879,7 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
     int32_t *d_status = reinterpret_cast<int32_t *>(w->d_tab + 4 * T);
     int32_t *h_status = reinterpret_cast<int32_t *>(w->h_tab + 4 * T);
     uint32_t *d_crc = reinterpret_cast<uint32_t *>(d_status) + T;
+    uint32_t *h_crc = reinterpret_cast<uint32_t *>(h_status) + T;  // pinned mirror (see host_encode_blocks_packed)
     // Chunk pipeline (see host_encode_blocks_packed): copy in, decode, checksum and copy
     // out run per chunk on their own streams.  Source ranges must be ascending for the
     // per-chunk H2D; otherwise the batch goes as one chunk.
@@ -911,7 +917,7 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
         if (crc_out) {  // checksum of the decoded blocks while they are resident (reader.go:341-351)
             rc = launch_crc(device, m, w->d_dst, w->d_tab + 2 * T + f, w->d_tab + 3 * T + f, d_crc + f, cs);
             if (rc) return rc;
-            CU_TRY(cudaMemcpyAsync(crc_out + f, d_crc + f, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+            CU_TRY(cudaMemcpyAsync(h_crc + f, d_crc + f, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
         }
         CU_TRY(cudaMemcpyAsync(h_status + f, d_status + f, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
         if (dense) {
@@ -928,6 +934,7 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
     CU_TRY(cudaEventRecord(w->ev1, w->stream));
     CU_TRY(cudaStreamSynchronize(w->stream));
     for (int i = 0; i < nblk; i++) status[i] = h_status[i];
+    if (crc_out) memcpy(crc_out, h_crc, (size_t)nblk * sizeof(uint32_t));
     cudaEventElapsedTime(&g_last_kernel_ms, w->ev0, w->ev1);
     return MZCU_OK;
 }

@@ -300,7 +300,10 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
         st->lx_ready[0][lane] = st->lx_ready[1][lane] = 0;
         st->lx_lexed[0][lane] = st->lx_lexed[1][lane] = 0;
     }
-    if (threadIdx.x < kDecLexers) mbar_init(&lexer_bar[threadIdx.x], 1);
+    if (threadIdx.x < kDecLexers) {
+        mbar_init(&lexer_bar[threadIdx.x], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the copy engine and to the other warps
+    }
     if (threadIdx.x < 256) st->lut[threadIdx.x] = dec_lut_entry(threadIdx.x);
     if (threadIdx.x < kDecSlots) {
         st->count[0][threadIdx.x] = st->count[1][threadIdx.x] = 0;
@@ -350,7 +353,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                         // ---- cold path ----
                         uint32_t where = 0;
                         uint64_t w8;
-                        if (a + 8 <= p_ready || p_aend <= p_ready) {
+                        if (a + 12 <= p_ready || p_aend <= p_ready) {
                             const uint32_t *rw = reinterpret_cast<const uint32_t *>(p_ring);
                             const uint32_t a4 = (uint32_t)a >> 2;
                             const uint32_t w0 = rw[a4 & (kDecRing / 4 - 1)], w1 = rw[(a4 + 1) & (kDecRing / 4 - 1)],
@@ -432,6 +435,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
             // rounds are long (the copiers): wait for the bytes and lex them right away
             if (lane == 0) mbar_arrive_expect_tx(lx_bar, lx_tx);
             mbar_wait(lx_bar, (unsigned)round & 1u);
+            __syncwarp();  // lane 0's lx_fill stores are read by every lane below
             // pass 2: token lengths.  adv[i] = header + literal bytes of a token that starts at byte i,
             // 0 when the length is extended (parser's cold path).  An entry needs bytes i, i+1; four
             // offsets per lane per step from two aligned words.
@@ -443,9 +447,12 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 if (done < (cur & ~15)) done = cur & ~15;  // bytes behind the cursor are dead
                 const uint32_t *ring = reinterpret_cast<const uint32_t *>(rings + (size_t)slot * kDecRing);
                 uint32_t *adv = reinterpret_cast<uint32_t *>(advs + (size_t)slot * kDecRing);
-                // the frontier stays 8 bytes behind what has landed (the copiers take 8 header bytes of a
-                // lexed token from the ring), or reaches the end of the stream
-                const int lim = afill >= aend ? aend : afill - 8;
+                // The frontier stays 12 bytes behind what has landed: parser and copiers take the 8 header
+                // bytes of a lexed token from the ring with three aligned word loads (<= 11 bytes from its
+                // start), and those must never touch cells the copy engine is filling.  It moves in whole
+                // words (an entry word is written once, never while the parser may read it) until it
+                // reaches the end of the stream.
+                const int lim = afill >= aend ? aend : (afill - 12) & ~3;
                 for (int i = (done & ~3) + 4 * lane; i < lim; i += 4 * 32) {
                     const uint32_t w0 = ring[(i >> 2) & (kDecRing / 4 - 1)], w1 = ring[((i >> 2) + 1) & (kDecRing / 4 - 1)];
                     uint32_t out = 0;

@@ -743,15 +743,30 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
         // ---- a verified candidate (:223-326; gen.go:1692-1978) ----
         const int from = kind == 2 ? L + 1 : L;
         int candidate = __shfl_sync(kFullMask, kind == 1 ? kS : (kind == 2 ? kN : kL), from);
-        if (kind == 2) s++;
+        // what the 8-byte snapshot of a long candidate already says about the match length:
+        // 4..7 = it ends there, 8 = at least 8 (a short-table candidate only vouches for 4)
+        int flen = 4;
         {
+            const uint64_t x = cv ^ (kind == 2 ? wN : wL);
+            if (kind != 1) flen = (uint32_t)(x >> 32) ? 4 + ((__ffs((int)(uint32_t)(x >> 32)) - 1) >> 3) : 8;
+            flen = __shfl_sync(kFullMask, flen, from);
+        }
+        if (kind == 2) s++;
+        // backward (:223-226) and forward (:239-254) extension in ONE round trip: the byte before the
+        // candidate is requested together with the forward bytes; only when it matches (5 %) does the
+        // backward loop run
+        bool beq = false;
+        if (lane == 0 && candidate > 0 && s > nextEmit) beq = src[candidate - 1] == src[s - 1];
+        const int pe = (kind != 1 && flen < 8) ? s + flen : extend_to_end(src, n, s + flen, candidate + flen, lane);
+        beq = __shfl_sync(kFullMask, (int)beq, 0);
+        if (beq) {
             const int back = extend_backward(src, candidate, s, nextEmit, lane);
             candidate -= back;
             s -= back;
         }
         const int base = s;
         const int offset = base - candidate;
-        s = extend_to_end(src, n, s + 4, candidate + 4, lane);
+        s = pe;
         if (kGo ? (offset > 65535 && s - base <= 4 && repeat != offset)                              // :257-264
                 : (P.far3 && s - base == 4 && offset > kMaxCopy2Offset && offset != repeat)) {       // gen.go:1786-1801
             s = nextS + 1;
