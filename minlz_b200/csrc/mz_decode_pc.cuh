@@ -453,6 +453,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 // words (an entry word is written once, never while the parser may read it) until it
                 // reaches the end of the stream.
                 const int lim = afill >= aend ? aend : (afill - 12) & ~3;
+                if (lim > done)  // (an entry word is never rewritten: the parser may be reading it)
                 for (int i = (done & ~3) + 4 * lane; i < lim; i += 4 * 32) {
                     const uint32_t w0 = ring[(i >> 2) & (kDecRing / 4 - 1)], w1 = ring[((i >> 2) + 1) & (kDecRing / 4 - 1)];
                     uint32_t out = 0;

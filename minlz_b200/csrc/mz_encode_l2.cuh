@@ -685,6 +685,7 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
                     if (!kGo && P.clamp && k2 <= p - 1 - kMaxCopy3Offset + 2) k2 = p - 1 - kMaxCopy3Offset + 2, w2 = ldg_u64_unaligned(src + k2);
                     f = (kGo ? k2 > p - 1 - kMaxCopy3Offset + 1 : true) && (uint32_t)cv == (uint32_t)w2;
                     kN = k2;
+                    wN = w2;
                 }
                 mn = (mn & ~(bitL << 1)) | (__ballot_sync(kFullMask, f) & (bitL << 1));
             }
