@@ -201,7 +201,8 @@ int init_device(int device) {
 
 // ---- launches --------------------------------------------------------------
 int launch_decode(int device, int nblk, const uint8_t *src, const uint64_t *sbeg, const uint64_t *send, uint8_t *dst,
-                  const uint64_t *dbeg, const uint64_t *dend, int32_t *status, cudaStream_t stream, int batch_blocks = 0) {
+                  const uint64_t *dbeg, const uint64_t *dend, int32_t *status, cudaStream_t stream, int batch_blocks = 0,
+                  bool record_done = true) {
     if (nblk == 0) return MZCU_OK;
     // up to 32 blocks per CTA (one parser lane each), spread over all SMs.  When this
     // launch is one chunk of a larger batch whose chunks run concurrently, size the
@@ -213,15 +214,13 @@ int launch_decode(int device, int nblk, const uint8_t *src, const uint64_t *sbeg
     if (slots > mz::kDecSlots) slots = mz::kDecSlots;
     if (slots < 1) slots = 1;
     const int grid = (nblk + slots - 1) / slots;
-    gate_enter();
     mz::decode_pc_kernel<<<grid, mz::kDecThreads, mz::kDecSmemBytes, stream>>>(nblk, slots, src, sbeg, send, dst, dbeg,
                                                                                dend, status);
     cudaError_t le = cudaGetLastError();
-    if (le == cudaSuccess) {
+    if (le == cudaSuccess && record_done) {
         std::lock_guard<std::mutex> lk(g_dev[device].order_mu);
         le = cudaEventRecord(g_dev[device].dec_done, stream);
     }
-    gate_leave();
     if (le != cudaSuccess) return fail(MZCU_ERR_CUDA, "decode launch: %s", cudaGetErrorString(le));
     return MZCU_OK;
 }
@@ -423,6 +422,7 @@ struct Workspace {
     cudaStream_t cs[kMaxChunks] = {};  // chunk pipelines (copy in / kernels / copy out overlap across chunks)
     cudaEvent_t tab_ready = nullptr;
     cudaEvent_t copied = nullptr;  // sliced upload: the last slice has landed
+    cudaEvent_t chunk_ev[kMaxChunks] = {};  // decode: the chunk's kernel is done
     int *d_arrived = nullptr;  // arrival gate of the sliced host->device source copy
     int *h_slice_no = nullptr; // pinned 1, 2, 3, ... (source of the gate writes)
 };
@@ -450,6 +450,7 @@ int ws_acquire(int device, Workspace **out) {
     for (int c = 0; c < kMaxChunks && e == cudaSuccess; c++) e = cudaStreamCreateWithFlags(&w->cs[c], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->tab_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->copied, cudaEventDisableTiming);
+    for (int c = 0; c < kMaxChunks && e == cudaSuccess; c++) e = cudaEventCreateWithFlags(&w->chunk_ev[c], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&w->d_arrived, sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_slice_no, kMaxSlices * sizeof(int));
     if (e == cudaSuccess)
@@ -895,6 +896,13 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
     CU_TRY(cudaMemcpyAsync(w->d_tab, w->h_tab, 4 * T * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream));
     CU_TRY(cudaEventRecord(w->tab_ready, w->stream));
     CU_TRY(cudaEventRecord(w->ev0, w->stream));
+    // Asynchronous jobs reach the device in submission order, a whole call at a time: every launch of
+    // this call is enqueued before a later job may launch (an encode launched in between would hold all
+    // SMs while the remaining chunks of this decode wait behind it).
+    gate_enter();
+    struct GateGuard {
+        ~GateGuard() { gate_leave(); }
+    } gate_guard;
     for (int c = 0; c < nchunks; c++) {
         cudaStream_t cs = w->cs[c];
         const int f = first[c], l = first[c + 1], m = l - f;
@@ -912,8 +920,9 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
         }
         if (chi > clo && clo != ~0ull) CU_TRY(cudaMemcpyAsync(w->d_src + clo, src + lo + clo, chi - clo, cudaMemcpyHostToDevice, cs));
         rc = launch_decode(device, m, w->d_src, w->d_tab + f, w->d_tab + T + f, w->d_dst, w->d_tab + 2 * T + f,
-                           w->d_tab + 3 * T + f, d_status + f, cs, nblk);
+                           w->d_tab + 3 * T + f, d_status + f, cs, nblk, false);
         if (rc) return rc;
+        CU_TRY(cudaEventRecord(w->chunk_ev[c], cs));
         if (crc_out) {  // checksum of the decoded blocks while they are resident (reader.go:341-351)
             rc = launch_crc(device, m, w->d_dst, w->d_tab + 2 * T + f, w->d_tab + 3 * T + f, d_crc + f, cs);
             if (rc) return rc;
@@ -930,6 +939,13 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
             }
         }
     }
+    // "every decode kernel of this call is done" for the encode launches that follow (DeviceState::dec_done)
+    for (int c = 0; c < nchunks; c++) CU_TRY(cudaStreamWaitEvent(w->stream, w->chunk_ev[c], 0));
+    {
+        std::lock_guard<std::mutex> lk(g_dev[device].order_mu);
+        CU_TRY(cudaEventRecord(g_dev[device].dec_done, w->stream));
+    }
+    gate_leave();
     for (int c = 0; c < nchunks; c++) CU_TRY(cudaStreamSynchronize(w->cs[c]));
     CU_TRY(cudaEventRecord(w->ev1, w->stream));
     CU_TRY(cudaStreamSynchronize(w->stream));

@@ -613,6 +613,8 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
             wvalid = true;
             const int p = wb + lane;
             cv = ld64_clamped(src, p, n);
+            // the next window's source bytes: its hashes (and so its probes) wait for them
+            if (lane < 2 && wb + 192 + 128 * lane < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + wb + 192 + 128 * lane));
             hL = P.hashL(cv);
             hS = P.hashS(cv);
             const uint4 el = lTable[hL];
@@ -640,13 +642,12 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
         uint32_t wS = vS;
         int kN = cL;           // ... and as the long probe at s+1 of the step at p-1 sees them
         uint64_t wN = vL;
-        bool f8, f4l, f4s, fr, fn;
+        bool f8, f4l, f4s, fn;
         if (kGo) {
             const int minSrcPos = p - kMaxCopy3Offset + 1;  // :118
             f8 = kL > minSrcPos && cv == wL;                                   // :130
             f4l = kL >= minSrcPos && (uint32_t)cv == (uint32_t)wL;             // :199
             f4s = kS >= minSrcPos && (uint32_t)cv == wS;                       // :204
-            fr = repeat > 0 && (uint32_t)(cv >> 8) == rep4;                    // :139
             fn = kN > minSrcPos - 1 && (uint32_t)cv == (uint32_t)wN;           // :209 (minSrcPos of the step at p-1)
         } else {
             if (P.clamp) {  // CMOVLLE: compared (and matched) at the clamped position (8 MiB class only)
@@ -658,11 +659,10 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
             f8 = cv == wL;
             f4l = (uint32_t)cv == (uint32_t)wL;
             f4s = (uint32_t)cv == wS;
-            fr = (uint32_t)(cv >> 8) == rep4;
             fn = (uint32_t)cv == (uint32_t)wN;
         }
         const unsigned m8 = __ballot_sync(kFullMask, f8), m4l = __ballot_sync(kFullMask, f4l),
-                       m4s = __ballot_sync(kFullMask, f4s), mr = __ballot_sync(kFullMask, fr);
+                       m4s = __ballot_sync(kFullMask, f4s);
         unsigned mn = __ballot_sync(kFullMask, fn);
         const unsigned dupL = __ballot_sync(kFullMask, (sameL & ~self) != 0), dupS = __ballot_sync(kFullMask, (sameS & ~self) != 0);
         const unsigned bitL = 1u << L;
@@ -694,7 +694,9 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
         int kind;  // 0: long candidate of s, 1: short candidate of s, 2: long candidate of s+1
         if (m8 & bitL) {
             kind = 0;
-        } else if (mr & bitL) {  // repeat at s+1 (:139-196; gen.go:1445-1622)
+        } else if (__ballot_sync(kFullMask, (!kGo || repeat > 0) && (uint32_t)(cv >> 8) == rep4) & bitL) {
+            // repeat at s+1 (:139-196; gen.go:1445-1622).  The check is evaluated only when the 8-byte test
+            // failed: its bytes were requested after the previous match and need not have landed before
             int base = s + 1;
             base -= extend_backward(src, base - repeat, base, nextEmit, lane);
             s = extend_to_end(src, n, s + 5, s + 5 - repeat, lane);
