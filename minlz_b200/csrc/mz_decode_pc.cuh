@@ -97,6 +97,9 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+#ifndef MZ_DEC_BULK
+#define MZ_DEC_BULK 1
+#endif
 // ---- bulk copies (the TMA engine's 1-D form, SASS UBLKCP) with mbarrier completion -------------
 // One thread hands the copy engine a contiguous, 16-byte aligned stretch of global memory; the bytes
 // land in shared memory without passing through registers and signal an mbarrier by byte count.
@@ -418,6 +421,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                 const int want = min((aend + 15) & ~15, (keep + kDecRingAhead) & ~15);
                 uint8_t *ring = rings + (size_t)slot * kDecRing;
                 const uintptr_t abase = (uintptr_t)st->lx_abase[slot];
+#if MZ_DEC_BULK
                 // [afill, want) is contiguous in memory and 16-byte aligned at both ends: one bulk copy,
                 // two when it wraps around the ring
                 if (lane == 0 && want > afill) {
@@ -429,12 +433,22 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                         bulk_copy_g2s(ring, reinterpret_cast<const void *>(abase + (uintptr_t)afill + first), len - first, lx_bar);
                     lx_tx += len;
                 }
+#else  // the same bytes with per-lane 16-byte cp.async (kept for A/B and for racecheck, which models these)
+                for (int chunk = afill + 16 * lane; chunk < want; chunk += 16 * 32)
+                    cp_async16(ring + (chunk & (kDecRing - 1)), reinterpret_cast<const void *>(abase + (uintptr_t)chunk));
+#endif
                 if (want > afill) afill = want;
                 if (lane == 0) st->lx_fill[slot] = afill;
             }
             // rounds are long (the copiers): wait for the bytes and lex them right away
+#if MZ_DEC_BULK
             if (lane == 0) mbar_arrive_expect_tx(lx_bar, lx_tx);
             mbar_wait(lx_bar, (unsigned)round & 1u);
+#else
+            (void)lx_bar;
+            (void)lx_tx;
+            cp_async_wait_all();
+#endif
             __syncwarp();  // lane 0's lx_fill stores are read by every lane below
             // pass 2: token lengths.  adv[i] = header + literal bytes of a token that starts at byte i,
             // 0 when the length is extended (parser's cold path).  An entry needs bytes i, i+1; four
