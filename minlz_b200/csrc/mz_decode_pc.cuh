@@ -438,6 +438,7 @@ decode_pc_kernel(int nblk, int slots_per_cta, const uint8_t *__restrict__ src, c
                     cp_async16(ring + (chunk & (kDecRing - 1)), reinterpret_cast<const void *>(abase + (uintptr_t)chunk));
 #endif
                 if (want > afill) afill = want;
+                __syncwarp();  // every lane has read lx_fill[slot]
                 if (lane == 0) st->lx_fill[slot] = afill;
             }
             // rounds are long (the copiers): wait for the bytes and lex them right away
