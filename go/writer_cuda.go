@@ -22,14 +22,12 @@ import (
 // cudaBatchBlocks bounds one device call (pinned staging = 2 x batch bytes).
 const cudaBatchBlocks = 4096
 
+// cudaLevel reports whether the Writer's level (writer.go:135, switch at :573-582) is one
+// of the levels on the accelerated path.
 func (w *Writer) cudaLevel() (int, bool) {
-	switch w.level {
-	case levelSuperFast:
-		return LevelSuperFast, true
-	case levelFastest:
-		return LevelFastest, true
-	case levelBalanced:
-		return LevelBalanced, true
+	switch int(w.level) {
+	case LevelSuperFast, LevelFastest, LevelBalanced:
+		return int(w.level), true
 	}
 	return 0, false
 }

@@ -31,8 +31,9 @@
 //   * LEXER warps take everything off the parser's chain that is not the chain itself.  Where
 //     the next token starts depends on the previous token, but how long a token WOULD be if
 //     one started at byte i depends on bytes i, i+1 only: the lexers prefetch every slot's
-//     stream into a shared-memory ring (coalesced 16-byte cp.async, 32 lanes per slot) and
-//     fill adv[i] for every byte offset of it, lanes in parallel.  The parser's step is then
+//     stream into a shared-memory ring (one cp.async.bulk per slot and round, completed on an
+//     mbarrier; -DMZ_DEC_BULK=0: per-lane 16-byte cp.async) and fill adv[i] for every byte
+//     offset of it, lanes in parallel.  The parser's step is then
 //     i += adv[i] -- one shared-memory load -- plus the descriptor stores (~45 cycles per
 //     token instead of ~350).  Extended lengths (adv 0) and bytes not lexed yet take the
 //     parser's old path.

@@ -27,10 +27,15 @@
 //     forwarded between lanes (match.any on the slot index), and only the
 //     inserts of steps that really executed are written back.
 //   * source bytes near the cursor sit in a 1 KiB per-warp shared-memory ring.
-//   * what finally bounds it (profiles/r01_micro_gather32.txt): a random 32-byte
-//     probe costs a whole 128-byte DRAM line on B200, and 32 probes per round
-//     trip x 30 k round trips x 4096 blocks move 450 GB at 92 % of the rate the
-//     DRAM sustains for random lines.
+//   * a random 32-byte probe costs a whole 128-byte DRAM line on B200
+//     (profiles/r01_micro_gather32.txt), so a 1-bit tag per slot in shared memory
+//     keeps the lanes whose probe cannot verify from fetching theirs (-35 % DRAM
+//     bytes, profiles/r02_tag_filter_variants.txt).
+//   * what finally bounds it: every block is one warp and all of
+//     them run at once, so the kernel's time is ONE warp's chain -- 29 952 round
+//     trips per 1 MiB block, each a loaded DRAM round trip plus ~620 dependent
+//     instructions -- not the bytes moved (63 % issue utilisation, 45 % of the
+//     DRAM's copy rate).
 #pragma once
 
 #include "mz_common.cuh"

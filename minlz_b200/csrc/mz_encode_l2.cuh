@@ -10,8 +10,12 @@
 // Mapping: one block per warp, all blocks of the batch in flight at once; the
 // tables do not fit shared memory (and shared memory would cap the chip at ~148
 // chains of a latency-bound walk), so they live in a global-memory workspace slice
-// per warp.  Lanes 0-3 issue the independent probes of a step (long, short, repeat,
-// long at s+1) in one round trip; match extension is lane parallel.
+// per warp.  The walk (encode_l2_walk, one template for both flavours) probes a
+// window of 32 consecutive positions per DRAM round trip and steps through it on
+// the cached entries, which every insert of the walk patches; match extension and
+// the re-indexing of a match's interior are lane parallel.  The step-at-a-time
+// walks of round 1 (encode_l2_block / encode_l2_asm_block: lanes 0-3 issue the
+// probes of ONE step per round trip) are kept behind -DMZ_L2_REPLAY=0 for A/B.
 //
 // Table entries are SNAPSHOTS, as in the L1 kernel: a long-table entry is
 // {position, the 8 source bytes at it} (16 B), a short-table entry {position, 4
@@ -19,7 +23,8 @@
 // round trips per step) becomes one; the bytes are copies of immutable source
 // bytes, so every decision is unchanged.  An untouched (zero) entry stands for
 // candidate 0, whose bytes are src[0..8) (encode_l2.go:84,121-130).  2.1 MiB of
-// workspace per in-flight block.
+// workspace per in-flight block.  (Wider entries -- 12 bytes + the byte before the
+// position -- were measured and lost: profiles/r02_l2_wide_snapshot_negative.txt.)
 #pragma once
 
 #include "mz_common.cuh"
