@@ -119,10 +119,6 @@ struct DeviceState {
     // waits for the decode kernels already submitted on this device (<= one decode's duration) and
     // the download then overlaps the encode.
     cudaEvent_t dec_done = nullptr;
-    // ... and an encode's bulk upload (4x the decode's) yields to the uploads of the decode calls
-    // already submitted: sharing the H2D direction would double the time until the decode's kernels
-    // -- and with them the encode's own launch -- can run
-    cudaEvent_t dec_up_done = nullptr;
     std::mutex order_mu;
 };
 DeviceState g_dev[kMaxDevices];
@@ -176,7 +172,6 @@ int init_device(int device) {
                 cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st.dec_done, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st.dec_up_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&st.counters, kCounterSlots * sizeof(int));
         if (e == cudaSuccess) e = cudaMalloc(&st.crc_tabs, sizeof(mz::CrcTables));
         if (e == cudaSuccess) {
@@ -428,7 +423,6 @@ struct Workspace {
     cudaEvent_t tab_ready = nullptr;
     cudaEvent_t copied = nullptr;  // sliced upload: the last slice has landed
     cudaEvent_t chunk_ev[kMaxChunks] = {};  // decode: the chunk's kernel is done
-    cudaEvent_t up_ev[kMaxChunks] = {};     // decode: the chunk's upload is done
     int *d_arrived = nullptr;  // arrival gate of the sliced host->device source copy
     int *h_slice_no = nullptr; // pinned 1, 2, 3, ... (source of the gate writes)
 };
@@ -457,7 +451,6 @@ int ws_acquire(int device, Workspace **out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->tab_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->copied, cudaEventDisableTiming);
     for (int c = 0; c < kMaxChunks && e == cudaSuccess; c++) e = cudaEventCreateWithFlags(&w->chunk_ev[c], cudaEventDisableTiming);
-    for (int c = 0; c < kMaxChunks && e == cudaSuccess; c++) e = cudaEventCreateWithFlags(&w->up_ev[c], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&w->d_arrived, sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_slice_no, kMaxSlices * sizeof(int));
     if (e == cudaSuccess)
@@ -736,10 +729,6 @@ int host_encode_blocks_packed(int device, int level, int nblk, const uint8_t *sr
                                    w->d_arrived, (int)S);
                 if (rc) return rc;
                 CU_TRY(cudaStreamWaitEvent(cp, w->tab_ready, 0));  // the gate is zeroed before the first write
-                {
-                    std::lock_guard<std::mutex> lk(g_dev[device].order_mu);
-                    CU_TRY(cudaStreamWaitEvent(cp, g_dev[device].dec_up_done, 0));  // pending decode uploads first
-                }
                 cudaError_t ce = cudaSuccess;
                 for (int k = 0; k < nsl && ce == cudaSuccess; k++) {
                     const size_t o = (size_t)k * S, wd = o + S <= B ? S : B - o;
@@ -930,7 +919,6 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
             chi = hi - lo;
         }
         if (chi > clo && clo != ~0ull) CU_TRY(cudaMemcpyAsync(w->d_src + clo, src + lo + clo, chi - clo, cudaMemcpyHostToDevice, cs));
-        CU_TRY(cudaEventRecord(w->up_ev[c], cs));
         rc = launch_decode(device, m, w->d_src, w->d_tab + f, w->d_tab + T + f, w->d_dst, w->d_tab + 2 * T + f,
                            w->d_tab + 3 * T + f, d_status + f, cs, nblk, false);
         if (rc) return rc;
@@ -952,11 +940,9 @@ int host_decode_ranges(int device, int nblk, const uint8_t *src, const uint64_t 
         }
     }
     // "every decode kernel of this call is done" for the encode launches that follow (DeviceState::dec_done)
-    for (int c = 0; c < nchunks; c++) CU_TRY(cudaStreamWaitEvent(w->cs[kMaxChunks - 1], w->up_ev[c], 0));
     for (int c = 0; c < nchunks; c++) CU_TRY(cudaStreamWaitEvent(w->stream, w->chunk_ev[c], 0));
     {
         std::lock_guard<std::mutex> lk(g_dev[device].order_mu);
-        if (nchunks < kMaxChunks) CU_TRY(cudaEventRecord(g_dev[device].dec_up_done, w->cs[kMaxChunks - 1]));
         CU_TRY(cudaEventRecord(g_dev[device].dec_done, w->stream));
     }
     gate_leave();
