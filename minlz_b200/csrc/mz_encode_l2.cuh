@@ -47,8 +47,26 @@ constexpr size_t kEncL2WsBytesPerWarp = ((size_t)(1 << 17) * 16) + ((size_t)(1 <
 __device__ __forceinline__ void l2_put_long(uint4 *t, uint32_t h, int pos, uint64_t bytes) {
     t[h] = make_uint4((uint32_t)pos, (uint32_t)bytes, (uint32_t)(bytes >> 32), 0u);
 }
+// Optional 1-bit tag per short-table slot in shared memory (2 KiB per block), as in the L1 kernel:
+// a window probe whose tag differs from the tag of its own 4 bytes cannot verify and is not fetched.
+// (The long table would need 16 KiB per block and does not fit.)
+#ifndef MZ_L2_STAGS
+#define MZ_L2_STAGS 0
+#endif
+#if MZ_L2_STAGS
+__device__ __forceinline__ uint32_t *l2_stags() {
+    __shared__ uint32_t tags[kEncL2Warps][(1 << 14) / 32];
+    return tags[threadIdx.x >> 5];
+}
+__device__ __forceinline__ uint32_t l2_tag1(uint32_t v) { return (v * 2654435761u) >> 31; }
+#endif
 __device__ __forceinline__ void l2_put_short(uint2 *t, uint32_t h, int pos, uint64_t bytes) {
     t[h] = make_uint2((uint32_t)pos, (uint32_t)bytes);
+#if MZ_L2_STAGS
+    uint32_t *tg = l2_stags();
+    const uint32_t bit = 1u << (h & 31);
+    if (((tg[h >> 5] & bit) != 0) != (l2_tag1((uint32_t)bytes) != 0)) atomicXor(&tg[h >> 5], bit);
+#endif
 }
 
 // 8 bytes at pos, zero filled past n; never touches a word with no byte < n.
@@ -623,7 +641,14 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
             hL = P.hashL(cv);
             hS = P.hashS(cv);
             const uint4 el = lTable[hL];
-            const uint2 es = sTable[hS];
+            bool fetch_s = true;
+#if MZ_L2_STAGS
+            // (a far candidate of the clamped class is compared at its clamped position: always fetch there)
+            fetch_s = ((l2_stags()[hS >> 5] >> (hS & 31)) & 1u) == l2_tag1((uint32_t)cv) ||
+                      (!kGo && P.clamp && p >= kMaxCopy3Offset - 2);
+#endif
+            uint2 es = make_uint2(0u, ~(uint32_t)cv);  // not fetched: cannot verify
+            if (fetch_s) es = sTable[hS];
             repw = repeat;
             rep4 = (p + 5 <= n && p + 1 >= repeat) ? ldg_u32_unaligned(src + p + 1 - repeat) : 0;
             cL = (int)el.x;
@@ -631,7 +656,7 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
             cS = (int)es.x;
             vS = es.y;
             if (cL == 0) vL = src0;
-            if (cS == 0) vS = (uint32_t)src0;
+            if (cS == 0 && fetch_s) vS = (uint32_t)src0;
             sameL = __match_any_sync(kFullMask, hL);
             sameS = __match_any_sync(kFullMask, hS);
         }
@@ -848,6 +873,13 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
             for (int i = lane; i < (1 << cls.lBits); i += 32) lTable[i] = make_uint4(0, 0, 0, 0);
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
             for (int i = lane; i < (1 << cls.sBits) / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+#if MZ_L2_STAGS
+            {   // untouched short entries stand for candidate 0: every tag starts as the tag of src[0..4)
+                const uint32_t t0 = l2_tag1(ldg_u32_unaligned(sp)) ? 0xffffffffu : 0u;
+                uint32_t *tg = l2_stags();
+                for (int i = lane; i < (1 << 14) / 32; i += 32) tg[i] = t0;
+            }
+#endif
             __syncwarp();
 #if MZ_L2_REPLAY
             res = (n > (512 << 10) && n <= (2 << 20))
@@ -891,6 +923,13 @@ encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
             for (int i = lane; i < lents; i += 32) lTable[i] = make_uint4(0, 0, 0, 0);
             uint4 *s4 = reinterpret_cast<uint4 *>(sTable);
             for (int i = lane; i < sents / 2; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+#if MZ_L2_STAGS
+            {   // untouched short entries stand for candidate 0: every tag starts as the tag of src[0..4)
+                const uint32_t t0 = l2_tag1(ldg_u32_unaligned(sp)) ? 0xffffffffu : 0u;
+                uint32_t *tg = l2_stags();
+                for (int i = lane; i < (1 << 14) / 32; i += 32) tg[i] = t0;
+            }
+#endif
             __syncwarp();
 #if MZ_L2_REPLAY
             res = small ? encode_l2_walk(L2GoClass<true>(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
