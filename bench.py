@@ -669,11 +669,10 @@ def main():
             # the same round trip with the asynchronous calls (mzcu_submit_* / mzcu_wait): the decode of
             # batch k (download-heavy) overlaps the encode of batch k+1 (upload-heavy); second buffer set
             if not stored_leg and not args.no_pipeline:
-                if h2 is None:
-                    h2 = [torch.empty(nb * bs + 64, dtype=torch.uint8).pin_memory().numpy() for _ in range(2)] + \
-                         [torch.empty(nb * bs, dtype=torch.uint8).pin_memory().numpy()]
-                comps = [n_comp, h2[0]]
-                decs = [n_dec, h2[2]]
+                if h2 is None:  # one more packed-stream buffer: encode k+1 writes it while decode k reads the other
+                    h2 = torch.empty(nb * bs + 64, dtype=torch.uint8).pin_memory().numpy()
+                comps = [n_comp, h2]
+                decs = [n_dec, n_dec]  # decode k has been waited for before decode k+1 is submitted
                 hcs = [hc, np.zeros(nb + 1, dtype=np.uint64)]
                 crcs_a = [hcrc_a, np.zeros(nb, dtype=np.uint32)]
                 crcs_b = [hcrc_b, np.zeros(nb, dtype=np.uint32)]
@@ -704,8 +703,9 @@ def main():
                             je_ = sub_enc(i + 1)
                         assert lib.mzcu_wait(jd_) == 0, lib.mzcu_last_error()
 
+                n_dec[:] = 0
                 pipeline(2)
-                assert np.array_equal(decs[1], n_src) and not sts[1].any() and np.array_equal(decs[0], n_src)
+                assert np.array_equal(n_dec, n_src) and not sts[1].any() and not sts[0].any()
                 if dist is not None:
                     dist.barrier()
                 pk = max(2, min(K, 4))

@@ -972,11 +972,16 @@ int run_on_devices(int ndev, const int *devices, int nblk, F &&call) {
     for (int k = 0; k < ndev; k++) {
         const int lo = (int)((int64_t)nblk * k / ndev), hi = (int)((int64_t)nblk * (k + 1) / ndev);
         if (hi == lo) continue;
-        th.emplace_back([&, k, lo, hi] {
+        auto work = [&, k, lo, hi] {
             mzcu_bind_host_to_device(devices[k]);
             part[k].rc = call(devices[k], lo, hi);
             if (part[k].rc) snprintf(part[k].err, sizeof part[k].err, "device %d: %.480s", devices[k], g_err);
-        });
+        };
+        try {
+            th.emplace_back(work);
+        } catch (...) {  // no thread to be had: this range runs on the caller's thread
+            work();
+        }
     }
     for (auto &t : th) t.join();
     for (int k = 0; k < ndev; k++)
@@ -999,17 +1004,26 @@ template <class F>
 int64_t submit_job(F &&call) {
     Job *j = new Job();
     int bound = -1;
-    cudaGetDevice(&bound);
+    if (cudaGetDevice(&bound) != cudaSuccess) {
+        cudaGetLastError();
+        bound = -1;
+    }
     std::lock_guard<std::mutex> lk(g_job_mu);
-    const int64_t id = g_next_job++;
-    j->th = std::thread([j, call, bound, id] {
-        if (bound >= 0) cudaSetDevice(bound);
-        t_ticket = id;
-        j->rc = call();
-        if (j->rc) snprintf(j->err, sizeof j->err, "%s", g_err);
-        gate_enter();  // a job that never launched still takes (and passes on) its turn
-        gate_leave();
-    });
+    const int64_t id = g_next_job;
+    try {
+        j->th = std::thread([j, call, bound, id] {
+            if (bound >= 0) cudaSetDevice(bound);
+            t_ticket = id;
+            j->rc = call();
+            if (j->rc) snprintf(j->err, sizeof j->err, "%s", g_err);
+            gate_enter();  // a job that never launched still takes (and passes on) its turn
+            gate_leave();
+        });
+    } catch (...) {
+        delete j;
+        return fail(MZCU_ERR_INVALID_ARG, "cannot start a job thread");
+    }
+    g_next_job++;  // the ticket is taken only when its thread exists (the launch gate waits for every ticket)
     g_jobs[id] = j;
     return id;
 }
@@ -1331,7 +1345,7 @@ int mzcu_validate_blocks_dev(int device, int nblk, const uint8_t *src, const uin
 // exposes none / the device has no affinity -- in which case nothing is changed.
 int mzcu_bind_host_to_device(int device) {
     device = resolve_device(device);
-    if (device < 0) return fail(MZCU_ERR_CUDA, "no CUDA device");
+    if (device < 0) return -1;
     char bus[32] = "";
     if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
         cudaGetLastError();
