@@ -428,6 +428,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: blocking calls only")
+    ap.add_argument("--pipeline-ahead", default="1,2", help="e2e: encode jobs submitted ahead of the oldest decode (comma list)")
+    ap.add_argument("--pipeline-iters", type=int, default=0, help="e2e: batches per pipelined measurement (0: from --steps)")
     ap.add_argument("--no-gate", action="store_true", help="skip the all-blocks encoder byte comparison (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -606,9 +608,10 @@ def main():
         hcrc_a = np.zeros(nb, dtype=np.uint32)
         hcrc_b = np.zeros(nb, dtype=np.uint32)
         e2e_tot = {"enc": 0.0, "dec": 0.0, "t": 0.0, "cb": 0, "bytes": 0}
-        h2 = None
-        pipe_t = 0.0
-        pipe_bytes = 0
+        extra = []
+        aheads = sorted({max(1, int(a)) for a in args.pipeline_ahead.split(",")})
+        pipe_t = {a: 0.0 for a in aheads}
+        pipe_bytes = {a: 0 for a in aheads}
         api = ("mzcu_stream_encode_blocks + mzcu_stream_decode_blocks (host pointers, pinned, CRC-32C on the device)" if with_crc
                else "mzcu_encode_blocks_packed + mzcu_decode_blocks (host pointers, pinned)")
         for leg in legs:
@@ -666,71 +669,84 @@ def main():
             e2e_tot["bytes"] += nb * bs
             legs_out[leg]["e2e_gbps"] = round(world * nb * bs / float(tt[0]) / 1e9, 4)
 
-            # the same round trip with the asynchronous calls (mzcu_submit_* / mzcu_wait): the decode of
-            # batch k (download-heavy) overlaps the encode of batch k+1 (upload-heavy); second buffer set
+            # the same round trip with the asynchronous calls (mzcu_submit_* / mzcu_wait): `ahead` encode
+            # jobs are in flight before the decode of the oldest one is submitted, so the device always has
+            # the next kernel queued (launch order = submission order) and the download of one call overlaps
+            # the upload and the kernels of the next.  ahead + 1 packed-stream buffers; one decoded buffer
+            # (decode k has been waited for before decode k+1 is submitted).
             if not stored_leg and not args.no_pipeline:
-                if h2 is None:  # one more packed-stream buffer: encode k+1 writes it while decode k reads the other
-                    h2 = torch.empty(nb * bs + 64, dtype=torch.uint8).pin_memory().numpy()
-                comps = [n_comp, h2]
-                decs = [n_dec, n_dec]  # decode k has been waited for before decode k+1 is submitted
-                hcs = [hc, np.zeros(nb + 1, dtype=np.uint64)]
-                crcs_a = [hcrc_a, np.zeros(nb, dtype=np.uint32)]
-                crcs_b = [hcrc_b, np.zeros(nb, dtype=np.uint32)]
-                sts = [hst, np.zeros(nb, dtype=np.int32)]
+                need = cb + 64
+                while len(extra) < aheads[-1] or any(x.size < need for x in extra):
+                    extra = [x for x in extra if x.size >= need]
+                    extra.append(torch.empty(need, dtype=torch.uint8).pin_memory().numpy())
+                comps = [n_comp] + extra[: aheads[-1]]
+                hcs = [hc] + [np.zeros(nb + 1, dtype=np.uint64) for _ in range(aheads[-1])]
+                crcs_a = [hcrc_a] + [np.zeros(nb, dtype=np.uint32) for _ in range(aheads[-1])]
+                crcs_b = [hcrc_b] + [np.zeros(nb, dtype=np.uint32) for _ in range(aheads[-1])]
+                sts = [hst] + [np.zeros(nb, dtype=np.int32) for _ in range(aheads[-1])]
 
-                def sub_enc(i):
-                    b_ = i & 1
+                def sub_enc(i, nbuf):
+                    b_ = i % nbuf
                     j_ = lib.mzcu_submit_stream_encode_blocks(local, args.level, nb, n_src.ctypes.data, hs.ctypes.data,
                                                               comps[b_].ctypes.data, comps[b_].size, hcs[b_].ctypes.data,
                                                               crcs_a[b_].ctypes.data if with_crc else None)
-                    assert j_ > 0
+                    assert j_ > 0, lib.mzcu_last_error()
                     return j_
 
-                def sub_dec(i):
-                    b_ = i & 1
+                def sub_dec(i, nbuf):
+                    b_ = i % nbuf
                     j_ = lib.mzcu_submit_stream_decode_blocks(local, nb, comps[b_].ctypes.data, hcs[b_].ctypes.data,
-                                                              decs[b_].ctypes.data, hs.ctypes.data, sts[b_].ctypes.data,
+                                                              n_dec.ctypes.data, hs.ctypes.data, sts[b_].ctypes.data,
                                                               crcs_b[b_].ctypes.data if with_crc else None)
-                    assert j_ > 0
+                    assert j_ > 0, lib.mzcu_last_error()
                     return j_
 
-                def pipeline(nit):
-                    je_ = sub_enc(0)
+                def pipeline(nit, ahead):
+                    nbuf = ahead + 1
+                    je_ = {i: sub_enc(i, nbuf) for i in range(min(ahead, nit))}
                     for i in range(nit):
-                        assert lib.mzcu_wait(je_) == 0, lib.mzcu_last_error()
-                        jd_ = sub_dec(i)
-                        if i + 1 < nit:
-                            je_ = sub_enc(i + 1)
+                        assert lib.mzcu_wait(je_.pop(i)) == 0, lib.mzcu_last_error()
+                        jd_ = sub_dec(i, nbuf)
+                        if i + ahead < nit:
+                            je_[i + ahead] = sub_enc(i + ahead, nbuf)
                         assert lib.mzcu_wait(jd_) == 0, lib.mzcu_last_error()
 
-                n_dec[:] = 0
-                pipeline(2)
-                assert np.array_equal(n_dec, n_src) and not sts[1].any() and not sts[0].any()
-                if dist is not None:
-                    dist.barrier()
-                pk = max(2, min(K, 4))
-                t0 = time.perf_counter()
-                pipeline(pk)
-                dtp = (time.perf_counter() - t0) / pk
-                tp_ = torch.tensor([dtp], dtype=torch.float64, device=dev)
-                if dist is not None:
-                    dist.all_reduce(tp_, op=dist.ReduceOp.MAX)
-                pipe_t += float(tp_[0])
-                pipe_bytes += nb * bs
+                for ahead in aheads:
+                    n_dec[:] = 0
+                    pipeline(ahead + 1, ahead)
+                    assert np.array_equal(n_dec, n_src) and not any(s_.any() for s_ in sts[: ahead + 1])
+                    if with_crc:
+                        assert all(np.array_equal(hcrc_a, c_) for c_ in crcs_a[: ahead + 1] + crcs_b[: ahead + 1])
+                    if dist is not None:
+                        dist.barrier()
+                    pk = args.pipeline_iters or 4 * (ahead + 1)  # 8 / 12 batches of 4 GiB: a 32 - 48 GiB stream
+                    t0 = time.perf_counter()
+                    pipeline(pk, ahead)
+                    dtp = (time.perf_counter() - t0) / pk
+                    tp_ = torch.tensor([dtp], dtype=torch.float64, device=dev)
+                    if dist is not None:
+                        dist.all_reduce(tp_, op=dist.ReduceOp.MAX)
+                    pipe_t[ahead] += float(tp_[0])
+                    pipe_bytes[ahead] += nb * bs
         nl = len(legs)
         dec_legs = sum(1 for leg in legs if leg != "random")
         serial_v = round(world * e2e_tot["bytes"] / e2e_tot["t"] / 1e9, 4)
-        pipe_v = round(world * pipe_bytes / pipe_t / 1e9, 4) if pipe_t > 0 and pipe_bytes == e2e_tot["bytes"] else None
+        pipe_vs = {a: round(world * pipe_bytes[a] / pipe_t[a] / 1e9, 4)
+                   for a in pipe_t if pipe_t[a] > 0 and pipe_bytes[a] == e2e_tot["bytes"]}
+        ahead_best = max(pipe_vs, key=pipe_vs.get) if pipe_vs else None
+        pipe_v = pipe_vs[ahead_best] if pipe_vs else None
         e2e = {"value": pipe_v if pipe_v and pipe_v > serial_v else serial_v, "unit": UNIT,
                "serial_calls": serial_v, "pipelined_calls": pipe_v,
-               "how": "value = the better of: one blocking encode call then one blocking decode call per step (serial_calls); "
-                      "the same calls submitted asynchronously (mzcu_submit_* / mzcu_wait), decode of batch k overlapping "
-                      "encode of batch k+1 (pipelined_calls).  Both move every input and output byte over PCIe inside "
-                      "the timed region.",
+               "pipelined_by_jobs_in_flight": {str(a + 1): v for a, v in pipe_vs.items()},
+               "how": "value = the best of: one blocking encode call then one blocking decode call per step (serial_calls); "
+                      "the same calls submitted asynchronously (mzcu_submit_* / mzcu_wait) with two or three jobs in "
+                      "flight - the decode of batch k overlaps the encodes of batches k+1 (and k+2) - ramp-up and drain "
+                      "inside the timed region (pipelined_calls).  All of them move every input and output byte over PCIe "
+                      "inside the timed region.",
                "h2d_bytes_per_step": int(e2e_tot["bytes"] + e2e_tot["cb"] + nl * 2 * 8 * (nb + 1) * 2),
                "d2h_bytes_per_step": int(e2e_tot["cb"] + dec_legs * nb * bs + nl * 8 * nb),
                "blocks_per_step": nb * nl,
-               "ms_per_step": round((pipe_t if pipe_v and pipe_v > serial_v else e2e_tot["t"]) * 1e3, 3),
+               "ms_per_step": round((pipe_t[ahead_best] if pipe_v and pipe_v > serial_v else e2e_tot["t"]) * 1e3, 3),
                "serial_ms_per_step": round(e2e_tot["t"] * 1e3, 3),
                "encode_call_ms": round(e2e_tot["enc"] * 1e3, 3), "decode_call_ms": round(e2e_tot["dec"] * 1e3, 3),
                "api": api}
