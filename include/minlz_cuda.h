@@ -207,7 +207,10 @@ int mzcu_stream_decode_blocks_multi(int ndev, const int *devices, int nblk, cons
  * handed over in order while later blocks still encode).  The batch analogue: submit returns a
  * job id (> 0) at once; the call runs on a library thread with its own workspace and streams, so
  * the D2H of batch k overlaps the H2D and kernels of batch k+1.  mzcu_wait blocks, returns the
- * call's result and retires the job.  All buffers must stay valid until mzcu_wait returns. */
+ * call's result and retires the job.  All buffers must stay valid until mzcu_wait returns.
+ * Jobs reach the device in submission order (their kernels are launched in that order), so a host
+ * decides the overlap by the order it submits in; three jobs in flight - encode k+1 and k+2
+ * submitted before decode k - keep the device and both PCIe directions busy. */
 int64_t mzcu_submit_stream_encode_blocks(int device, int level, int nblk, const uint8_t *src, const uint64_t *src_off,
                                          uint8_t *dst, size_t dst_cap, uint64_t *dst_off_out, uint32_t *crc_out);
 int64_t mzcu_submit_stream_decode_blocks(int device, int nblk, const uint8_t *src, const uint64_t *src_off, uint8_t *dst,
