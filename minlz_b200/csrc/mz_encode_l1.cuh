@@ -528,9 +528,19 @@ __device__ unsigned long long g_enc_stats[16];
 #define ENC_STAT(i) ((void)0)
 #endif
 
-constexpr int kEncL1Warps = 4;  // warps per CTA
+// One warp per CTA: a block is encoded by one warp and the warps share nothing, so the CTA is only a
+// container -- and with a single warp in it every shared-memory address below (ring, records, tags) is a
+// compile-time constant.  With four warps per CTA the kernel carried the per-warp pointers in registers
+// it did not have: 172 bytes of spills and ~36 instructions per batch recomputing shared-memory
+// addresses (S2R, in front of the probe loads).  Same 72-register budget, no spills:
+// 106.9 -> 92.5 ms (amd64 flavour), 108.8 -> 94.7 ms (Go) on 4096 x 1 MiB
+// (profiles/r02_one_warp_per_cta_l1_l2.txt, r02_l1_one_warp_per_cta.txt; two warps per CTA change nothing).
+#ifndef MZ_ENC_L1_WARPS
+#define MZ_ENC_L1_WARPS 1
+#endif
+constexpr int kEncL1Warps = MZ_ENC_L1_WARPS;  // warps per CTA
 #ifndef MZ_ENC_L1_MIN_CTAS
-#define MZ_ENC_L1_MIN_CTAS 7  // 28 warps per SM x 148 SMs >= 4096 blocks in flight, 72 registers
+#define MZ_ENC_L1_MIN_CTAS (28 / MZ_ENC_L1_WARPS)  // 28 warps per SM x 148 SMs >= 4096 blocks in flight, 72 registers
 #endif
 constexpr int kEncL1SlotsPerWarp = 1 << 15;
 constexpr size_t kEncL1WsBytesPerWarp = (size_t)kEncL1SlotsPerWarp * sizeof(Slot) + kTagWordsPerWarp * 4;  // 1 MiB of slots + the tags
@@ -1153,8 +1163,8 @@ encode_l1_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                  uint32_t *__restrict__ out_len, int *counter, Slot *tables, const int *gate, int slice) {
     __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror + 3 * kRecRing];
-    const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
+    const int lane = kEncL1Warps == 1 ? (int)threadIdx.x : lane_id();
+    const int warp = kEncL1Warps == 1 ? 0 : (int)(threadIdx.x >> 5);
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
     Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
     // the tag tables of all warps lie together behind the slots (dense: they are meant to stay in L2)
@@ -1197,8 +1207,8 @@ encode_l1_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
                      const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                      uint32_t *__restrict__ out_len, int *counter, Slot *tables, const int *gate, int slice) {
     __shared__ uint32_t rings[kEncL1Warps][kRingWords + kRingMirror + 3 * kRecRing];
-    const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
+    const int lane = kEncL1Warps == 1 ? (int)threadIdx.x : lane_id();
+    const int warp = kEncL1Warps == 1 ? 0 : (int)(threadIdx.x >> 5);
     const int gwarp = blockIdx.x * kEncL1Warps + warp;
     Slot *table = tables + (size_t)gwarp * kEncL1SlotsPerWarp;
     // the tag tables of all warps lie together behind the slots (dense: they are meant to stay in L2)

@@ -40,7 +40,15 @@ struct L2Params {
     __device__ static __forceinline__ uint32_t hashS(uint64_t u) { return hash4(u, kSBits); }
 };
 
-constexpr int kEncL2Warps = 4;
+// One warp per CTA, as in the LevelFastest kernel (mz_encode_l1.cuh): constant shared-memory addresses;
+// 319 -> 298 ms (amd64 flavour) / 301 ms (Go) on 4096 x 1 MiB (profiles/r02_one_warp_per_cta_l1_l2.txt).
+#ifndef MZ_ENC_L2_WARPS
+#define MZ_ENC_L2_WARPS 1
+#endif
+constexpr int kEncL2Warps = MZ_ENC_L2_WARPS;  // warps per CTA
+#ifndef MZ_ENC_L2_MIN_CTAS
+#define MZ_ENC_L2_MIN_CTAS (28 / MZ_ENC_L2_WARPS)  // 28 blocks in flight per SM, <= 72 registers
+#endif
 constexpr size_t kEncL2WsBytesPerWarp = ((size_t)(1 << 17) * 16) + ((size_t)(1 << 14) * 8);  // 2 MiB + 128 KiB
 
 // long-table entry {pos, 8 bytes at pos}; short-table entry {pos, 4 bytes at pos}
@@ -56,7 +64,7 @@ __device__ __forceinline__ void l2_put_long(uint4 *t, uint32_t h, int pos, uint6
 #if MZ_L2_STAGS
 __device__ __forceinline__ uint32_t *l2_stags() {
     __shared__ uint32_t tags[kEncL2Warps][(1 << 14) / 32];
-    return tags[threadIdx.x >> 5];
+    return tags[kEncL2Warps == 1 ? 0 : threadIdx.x >> 5];
 }
 __device__ __forceinline__ uint32_t l2_tag1(uint32_t v) { return (v * 2654435761u) >> 31; }
 #endif
@@ -849,13 +857,14 @@ __device__ int encode_l2_walk(const C P, uint8_t *dst, const uint8_t *src, const
     return d;
 }
 
-__global__ void __launch_bounds__(kEncL2Warps * 32)
+__global__ void __launch_bounds__(kEncL2Warps * 32, MZ_ENC_L2_MIN_CTAS)
 encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                      const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                      uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
     __shared__ uint32_t rec_rings[kEncL2Warps][3 * kRecRing];
-    const int lane = lane_id();
-    const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
+    const int lane = kEncL2Warps == 1 ? (int)threadIdx.x : lane_id();
+    const int warp = kEncL2Warps == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const int gwarp = blockIdx.x * kEncL2Warps + warp;
     uint4 *lTable = reinterpret_cast<uint4 *>(tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4));
     uint2 *sTable = reinterpret_cast<uint2 *>(lTable + (1 << 17));
     for (;;) {
@@ -883,12 +892,12 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
             __syncwarp();
 #if MZ_L2_REPLAY
             res = (n > (512 << 10) && n <= (2 << 20))
-                      ? encode_l2_walk(BetterAsm2MB(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
-                      : encode_l2_walk(cls, dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+                      ? encode_l2_walk(BetterAsm2MB(), dp, sp, n, lTable, sTable, rec_rings[warp], lane)
+                      : encode_l2_walk(cls, dp, sp, n, lTable, sTable, rec_rings[warp], lane);
 #else
             res = (n > (512 << 10) && n <= (2 << 20))
-                      ? encode_l2_asm_block(BetterAsm2MB(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
-                      : encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+                      ? encode_l2_asm_block(BetterAsm2MB(), dp, sp, n, lTable, sTable, rec_rings[warp], lane)
+                      : encode_l2_asm_block(cls, dp, sp, n, lTable, sTable, rec_rings[warp], lane);
 #endif
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
@@ -896,13 +905,14 @@ encode_l2_asm_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *
     }
 }
 
-__global__ void __launch_bounds__(kEncL2Warps * 32)
+__global__ void __launch_bounds__(kEncL2Warps * 32, MZ_ENC_L2_MIN_CTAS)
 encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__restrict__ sbeg,
                  const uint64_t *__restrict__ send, uint8_t *dst, const uint64_t *__restrict__ dbeg,
                  uint32_t *__restrict__ out_len, int *counter, uint32_t *tables) {
     __shared__ uint32_t rec_rings[kEncL2Warps][3 * kRecRing];
-    const int lane = lane_id();
-    const int gwarp = blockIdx.x * kEncL2Warps + (threadIdx.x >> 5);
+    const int lane = kEncL2Warps == 1 ? (int)threadIdx.x : lane_id();
+    const int warp = kEncL2Warps == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const int gwarp = blockIdx.x * kEncL2Warps + warp;
     uint4 *lTable = reinterpret_cast<uint4 *>(tables + (size_t)gwarp * (kEncL2WsBytesPerWarp / 4));
     uint2 *sTable = reinterpret_cast<uint2 *>(lTable + (1 << 17));
     for (;;) {
@@ -932,11 +942,11 @@ encode_l2_kernel(int nblk, const uint8_t *__restrict__ src, const uint64_t *__re
 #endif
             __syncwarp();
 #if MZ_L2_REPLAY
-            res = small ? encode_l2_walk(L2GoClass<true>(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
-                        : encode_l2_walk(L2GoClass<false>(), dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+            res = small ? encode_l2_walk(L2GoClass<true>(), dp, sp, n, lTable, sTable, rec_rings[warp], lane)
+                        : encode_l2_walk(L2GoClass<false>(), dp, sp, n, lTable, sTable, rec_rings[warp], lane);
 #else
-            res = small ? encode_l2_block<true>(dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane)
-                        : encode_l2_block<false>(dp, sp, n, lTable, sTable, rec_rings[threadIdx.x >> 5], lane);
+            res = small ? encode_l2_block<true>(dp, sp, n, lTable, sTable, rec_rings[warp], lane)
+                        : encode_l2_block<false>(dp, sp, n, lTable, sTable, rec_rings[warp], lane);
 #endif
         }
         if (lane == 0) out_len[blk] = (uint32_t)res;
